@@ -1,0 +1,139 @@
+/*
+ * qsb200.h -- C ABI of the B200-native two-body integral pipeline (libqsb200.so).
+ *
+ * Drop-in boundary for the hot path of HyQD/quantum-systems.  The reference has no FFI of its own
+ * (pure Python over numpy); each entry point below replaces the numpy call sites of one reference
+ * method, cited as `file:line` relative to /root/reference/quantum_systems/.  A maintainer binds
+ * them with ctypes; quantum_systems_b200/_native.py is that binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name says `host`; the library never allocates
+ *     or frees caller-visible memory, scratch is passed in (`workspace`);
+ *   - tensors are dense, C-contiguous (row-major); complex128 is interleaved (re, im) doubles;
+ *   - `stream` is a cudaStream_t passed as void* (0 = default stream); all work is enqueued
+ *     asynchronously on it;
+ *   - return value 0 = success, anything else = failure with text in qs_last_error();
+ *   - there is no CPU fallback: without a CUDA device every compute entry fails.
+ */
+#ifndef QSB200_H
+#define QSB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QS_F64 0  /* real float64 */
+#define QS_C128 1 /* complex128, interleaved */
+
+#define QS_OK 0
+#define QS_ERR_INVALID 1
+#define QS_ERR_CUDA 2
+#define QS_ERR_WORKSPACE 3
+
+/* Library identification and error text (thread-local, valid until the next failing call). */
+int qs_version(void);
+const char* qs_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Four-index transform   u'_pqrs = sum_abcd Ct[p,a] Ct[q,b] u[a,b,c,d] C[c,r] C[d,s]
+ * replaces BasisSet.transform_two_body_elements (basis_set.py:336-350): four quarter steps in the
+ * order s, r, q, p, each an (X x K)*(K x W) FP64 DMMA GEMM whose epilogue stores the new index as
+ * the slowest axis, so no separate permutation pass exists.
+ *
+ *   u      : (n, n, n, n)                dtype u_dtype
+ *   C      : (n, n_new)  row-major       dtype c_dtype
+ *   Ct     : (n_new, n)  row-major       dtype c_dtype, or NULL for conj(C)^T (basis_set.py:338-339)
+ *   out    : (n_new,)*4                  complex128 if either input is complex, else float64
+ *   workspace : at least qs_transform_two_body_workspace_bytes() bytes, 1024-byte aligned
+ * ------------------------------------------------------------------------------------------- */
+int qs_transform_two_body_workspace_bytes(int64_t n, int64_t n_new, int u_dtype, int c_dtype,
+                                          int64_t* bytes);
+int qs_transform_two_body(const void* u, int u_dtype, const void* C, const void* Ct, int c_dtype,
+                          int64_t n, int64_t n_new, void* out, void* workspace,
+                          int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * One quarter step, exposed for the sharded (multi-GPU) schedule and for the grid Coulomb build.
+ *
+ *   out[ (w / w_inner) * sw1 + (w % w_inner) * sw0 + (x / x_inner) * sx1 + (x % x_inner) * sx0 ]
+ *       = sum_k A[x, k] * M[k, w]              x < X, k < K, w < W   (element strides of a_dtype/out)
+ *
+ * A is (X, K) row-major with row pitch `lda` elements.  M is described by (m, m_dtype, m_sk, m_sw,
+ * m_conj): M[k, w] = m[k * m_sk + w * m_sw], conjugated if m_conj.  The kernel consumes M through a
+ * fragment-ordered "coefficient image" built by qs_build_coeff_image into `image`
+ * (qs_coeff_image_bytes() bytes).  Output dtype is complex if A or M is complex.  The store strides
+ * are in units of OUTPUT ELEMENTS; the plain rotated store is x_inner = X, sx0 = 1, sx1 = 0,
+ * w_inner = 1, sw0 = 0, sw1 = X.
+ * ------------------------------------------------------------------------------------------- */
+int qs_coeff_image_bytes(int64_t K, int64_t W, int a_dtype, int m_dtype, int64_t* bytes);
+int qs_build_coeff_image(const void* m, int m_dtype, int64_t m_sk, int64_t m_sw, int m_conj,
+                         int64_t K, int64_t W, int a_dtype, void* image, void* stream);
+int qs_quarter_transform(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda,
+                         const void* image, int m_dtype, int64_t W, void* out, int64_t x_inner,
+                         int64_t sx0, int64_t sx1, int64_t w_inner, int64_t sw0, int64_t sw1,
+                         void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * One-body transform  h' = Ct (h C)   replaces BasisSet.transform_one_body_elements
+ * (basis_set.py:329-334).  h: (n, n); C: (n, n_new); Ct: (n_new, n) or NULL; out: (n_new, n_new).
+ * workspace: qs_transform_one_body_workspace_bytes() bytes, 1024-byte aligned.
+ * ------------------------------------------------------------------------------------------- */
+int qs_transform_one_body_workspace_bytes(int64_t n, int64_t n_new, int h_dtype, int c_dtype,
+                                          int64_t* bytes);
+int qs_transform_one_body(const void* h, int h_dtype, const void* C, const void* Ct, int c_dtype,
+                          int64_t n, int64_t n_new, void* out, void* workspace, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Spin doubling and anti-symmetrisation (memory-bound passes).
+ *
+ * qs_add_spin_two_body: U[2p+s1,2q+s2,2r+s3,2s+s4] = u[p,q,r,s] [s1==s3][s2==s4], optionally fused with
+ *   U - U.transpose(0,1,3,2).  Replaces BasisSet.add_spin_two_body (basis_set.py:772-774) followed
+ *   by BasisSet.anti_symmetrize_u (:776-778).  Only leading-index planes P in [p_begin, p_end) of the
+ *   (2l)^4 result are written (to out + 0, i.e. `out` points at the first plane of the shard), which is
+ *   the multi-GPU partition.  in_dtype -> out_dtype may widen F64 -> C128 (cast_to_complex, :298-319).
+ * qs_anti_symmetrize: out = u - u.transpose(0,1,3,2) on an (n,n,n,n) tensor, planes [p_begin,p_end).
+ * qs_add_spin_one_body: kron(h, I2) (:768-770).
+ * ------------------------------------------------------------------------------------------- */
+int qs_add_spin_two_body(const void* u, int in_dtype, int64_t l, void* out, int out_dtype,
+                         int anti_symmetrize, int64_t p_begin, int64_t p_end, void* stream);
+int qs_anti_symmetrize(const void* u, int dtype, int64_t n, void* out, int64_t p_begin,
+                       int64_t p_end, void* stream);
+int qs_add_spin_one_body(const void* h, int in_dtype, int64_t l, void* out, int out_dtype,
+                         void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fock matrices (warp-shuffle reductions over the occupied index).
+ *   general : f[p,q] = h[p,q] + sum_{i<n_occ} u[p,i,q,i]                    general_orbital_system.py:119-159
+ *   spatial : f[p,q] = h[p,q] + 2 sum_i u[p,i,q,i] - sum_i u[p,i,i,q]       spatial_orbital_system.py:150-190
+ * h, f: (n, n) dtype h_dtype (f is overwritten); u: (n,n,n,n) dtype u_dtype (F64 u with C128 h allowed).
+ * Rows p in [p_begin, p_end) only; `u` points at plane p_begin of the tensor, h and f at row 0.
+ * ------------------------------------------------------------------------------------------- */
+int qs_fock_general(const void* h, int h_dtype, const void* u, int u_dtype, int64_t n,
+                    int64_t n_occ, void* f, int64_t p_begin, int64_t p_end, void* stream);
+int qs_fock_spatial(const void* h, int h_dtype, const void* u, int u_dtype, int64_t n,
+                    int64_t n_occ, void* f, int64_t p_begin, int64_t p_end, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * ODQD grid Coulomb build  u_abcd = sum_pq C_pa C_qb C_pc C_qd alpha/sqrt((x_p-x_q)^2 + a^2)
+ * replaces the einsum of ODQD.setup_basis (quantum_dots/one_dim/one_dim_qd.py:275-280) with two
+ * chained DMMA GEMMs (T = D W, u = T D^T, D[(ac),p] = C_pa C_pc); the acbd -> abcd permutation is
+ * fused into the second epilogue and W is generated from the grid, never loaded.
+ *   Cmat : (Gp, l) float64, interior-grid eigenvectors;  grid : (Gp,) float64 interior points
+ *   u_out: (l,l,l,l) float64 C-contiguous;  workspace >= qs_odqd_coulomb_workspace_bytes()
+ * ------------------------------------------------------------------------------------------- */
+int qs_odqd_coulomb_workspace_bytes(int64_t l, int64_t Gp, int64_t* bytes);
+int qs_odqd_coulomb(const double* Cmat, const double* grid, double alpha, double a, int64_t l,
+                    int64_t Gp, double* u_out, void* workspace, int64_t workspace_bytes,
+                    void* stream);
+
+/* Roofline denominators measured in place: register-resident DMMA.8x8x4 loop (FP64 tensor pipe)
+ * and a streaming copy.  Host out-pointers. */
+int qs_probe_dmma_tflops(double* host_tflops, void* stream);
+int qs_probe_copy_gbs(double* host_gbs, void* scratch, int64_t scratch_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QSB200_H */

@@ -1,0 +1,131 @@
+// Shared device/host helpers for libqsb200 (sm_100a only).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/qsb200.h"
+
+// ---------------------------------------------------------------------------------------------
+// host-side error plumbing
+// ---------------------------------------------------------------------------------------------
+void qs_set_error(const char* fmt, ...);
+
+#define QS_CUDA(call)                                                                          \
+    do {                                                                                       \
+        cudaError_t _e = (call);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            qs_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__,     \
+                         __LINE__);                                                            \
+            return QS_ERR_CUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+
+#define QS_REQUIRE(cond, ...)                                                                  \
+    do {                                                                                       \
+        if (!(cond)) {                                                                         \
+            qs_set_error(__VA_ARGS__);                                                         \
+            return QS_ERR_INVALID;                                                             \
+        }                                                                                      \
+    } while (0)
+
+#define QS_LAUNCH_CHECK()                                                                      \
+    do {                                                                                       \
+        cudaError_t _e = cudaGetLastError();                                                   \
+        if (_e != cudaSuccess) {                                                               \
+            qs_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, \
+                         __LINE__);                                                            \
+            return QS_ERR_CUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+
+static inline int64_t qs_round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+static inline int64_t qs_ceil_div(int64_t v, int64_t m) { return (v + m - 1) / m; }
+static inline int qs_elem_doubles(int dtype) { return dtype == QS_C128 ? 2 : 1; }
+
+// Number of SMs of the current device (cached).
+int qs_sm_count();
+
+// Internal (not part of the C ABI): coefficient image of the ODQD shielded-Coulomb matrix.
+int qs_build_coulomb_image(const double* grid, double alpha, double a, int64_t Gp, void* image, void* stream);
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers: mbarrier, TMA (tensor and 1-D bulk), FP64 tensor-core MMA
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "QS_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra QS_DONE_%=;\n"
+        "bra QS_WAIT_%=;\n"
+        "QS_DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+
+// 2-D tiled TMA load: box at (c0 = fastest coordinate, c1) -> shared, completes on `bar`.
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1,
+                                            uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, "
+        "{%2, %3}], [%4];" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+
+// 1-D bulk copy global -> shared (size multiple of 16 B), completes on `bar`.
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes,
+                                             uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(dst),
+        "l"(src), "r"(bytes), "r"(bar)
+        : "memory");
+}
+
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// D(8x8) += A(8x4, row) * B(4x8, col) in FP64 on the tensor pipe; SASS: DMMA.8x8x4.
+// Lane (g = lane >> 2, t = lane & 3) supplies A[g][t], B[t][g] and owns D[g][2t], D[g][2t+1].
+__device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double2 lds_128(uint32_t addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+#endif  // __CUDACC__

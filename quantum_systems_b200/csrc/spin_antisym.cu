@@ -1,0 +1,245 @@
+// Spin doubling and anti-symmetrisation: HBM-bound passes.
+//
+//   qs_add_spin_two_body : BasisSet.add_spin_two_body (reference basis_set.py:772-774), optionally
+//                          fused with BasisSet.anti_symmetrize_u (:776-778) and cast_to_complex (:298-319)
+//   qs_anti_symmetrize   : BasisSet.anti_symmetrize_u alone
+//   qs_add_spin_one_body : BasisSet.add_spin_one_body (:768-770)
+//
+// Fused pass, per output plane (P = 2p+s1, Q = 2q+s2) and 32x32 tile of spatial (r, s):
+//   U[P,Q,2r+g,2s+d] = [s1==g][s2==d] A[r,s] - [s1==d][s2==g] A[s,r],   A = u[p,q,:,:]
+// The direct tile and the transposed partner tile are both read with coalesced rows and exchanged
+// through a padded shared-memory tile; every output element (zeros included) is written exactly once
+// with 16-byte vector stores.  Algorithmic traffic: read l^4 + write 16 l^4 elements.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kTile = 32;
+
+template <bool IN_COMPLEX>
+struct Elem;
+template <>
+struct Elem<false> {
+    double re;
+    static __device__ __forceinline__ Elem load(const double* p, long long i) { return {p[i]}; }
+    __device__ __forceinline__ double real() const { return re; }
+    __device__ __forceinline__ double imag() const { return 0.0; }
+};
+template <>
+struct Elem<true> {
+    double re, im;
+    static __device__ __forceinline__ Elem load(const double* p, long long i) {
+        const double2 v = reinterpret_cast<const double2*>(p)[i];
+        return {v.x, v.y};
+    }
+    __device__ __forceinline__ double real() const { return re; }
+    __device__ __forceinline__ double imag() const { return im; }
+};
+
+// grid: x = tile index over (r-tile, s-tile), y = q, z = P - p_begin ; block = (32, 8)
+template <bool IN_COMPLEX, bool OUT_COMPLEX, bool ANTISYM>
+__global__ void __launch_bounds__(256) add_spin_kernel(const double* __restrict__ u, double* __restrict__ out, int l,
+                                                        int tiles, long long p_begin) {
+    __shared__ double dre[kTile][kTile + 1], ere[kTile][kTile + 1];
+    __shared__ double dim_[IN_COMPLEX ? kTile : 1][kTile + 1], eim[IN_COMPLEX ? kTile : 1][kTile + 1];
+
+    const int tr = blockIdx.x / tiles, ts = blockIdx.x % tiles;
+    const int q = blockIdx.y;
+    const long long P = p_begin + blockIdx.z;
+    const int p = (int)(P >> 1), s1 = (int)(P & 1);
+    const int r0 = tr * kTile, s0 = ts * kTile;
+    const long long n = 2LL * l;
+    const double* A = u + ((long long)p * l + q) * l * l * (IN_COMPLEX ? 2 : 1);
+
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    // direct tile D[i][j] = A[r0+i, s0+j]; partner tile E[i][j] = A[s0+i, r0+j]
+    for (int i = ty; i < kTile; i += 8) {
+        if (r0 + i < l && s0 + tx < l) {
+            const Elem<IN_COMPLEX> v = Elem<IN_COMPLEX>::load(A, (long long)(r0 + i) * l + s0 + tx);
+            dre[i][tx] = v.real();
+            if (IN_COMPLEX) dim_[i][tx] = v.imag();
+        }
+        if (ANTISYM && s0 + i < l && r0 + tx < l) {
+            const Elem<IN_COMPLEX> v = Elem<IN_COMPLEX>::load(A, (long long)(s0 + i) * l + r0 + tx);
+            ere[i][tx] = v.real();
+            if (IN_COMPLEX) eim[i][tx] = v.imag();
+        }
+    }
+    __syncthreads();
+
+    const int s = s0 + tx;
+    if (s >= l) return;
+    constexpr int OD = OUT_COMPLEX ? 2 : 1;
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2) {
+        const long long Q = 2LL * q + s2;
+        double* plane = out + (((long long)blockIdx.z * n + Q) * n) * n * OD;
+        for (int i = ty; i < kTile; i += 8) {
+            const int r = r0 + i;
+            if (r >= l) break;
+            const double ar = dre[i][tx], ai = IN_COMPLEX ? dim_[i][tx] : 0.0;
+            const double br = ANTISYM ? ere[tx][i] : 0.0, bi = (ANTISYM && IN_COMPLEX) ? eim[tx][i] : 0.0;
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                // element d of the pair (S = 2s + d): direct if s1==g && s2==d, exchange if s1==d && s2==g
+                double vr[2], vi[2];
+#pragma unroll
+                for (int d = 0; d < 2; ++d) {
+                    const bool direct = (s1 == g) && (s2 == d);
+                    const bool exch = ANTISYM && (s1 == d) && (s2 == g);
+                    vr[d] = (direct ? ar : 0.0) - (exch ? br : 0.0);
+                    vi[d] = (direct ? ai : 0.0) - (exch ? bi : 0.0);
+                }
+                double* row = plane + ((2LL * r + g) * n + 2LL * s) * OD;
+                if (OUT_COMPLEX) {
+                    reinterpret_cast<double2*>(row)[0] = make_double2(vr[0], vi[0]);
+                    reinterpret_cast<double2*>(row)[1] = make_double2(vr[1], vi[1]);
+                } else {
+                    reinterpret_cast<double2*>(row)[0] = make_double2(vr[0], vr[1]);
+                }
+            }
+        }
+    }
+}
+
+// out[p,q,r,s] = u[p,q,r,s] - u[p,q,s,r]; grid: x = tile(r,s), y = q, z = p - p_begin; block (32, 8)
+template <bool COMPLEX>
+__global__ void __launch_bounds__(256) antisym_kernel(const double* __restrict__ u, double* __restrict__ out, int n,
+                                                       int tiles, long long p_begin) {
+    __shared__ double ere[kTile][kTile + 1];
+    __shared__ double eim[COMPLEX ? kTile : 1][kTile + 1];
+    const int tr = blockIdx.x / tiles, ts = blockIdx.x % tiles;
+    const int r0 = tr * kTile, s0 = ts * kTile;
+    const long long plane = (((long long)(p_begin + blockIdx.z) * n + blockIdx.y) * n) * n;
+    const long long oplane = (((long long)blockIdx.z * n + blockIdx.y) * n) * n;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    for (int i = ty; i < kTile; i += 8) {
+        if (s0 + i < n && r0 + tx < n) {
+            const long long idx = plane + (long long)(s0 + i) * n + r0 + tx;
+            if (COMPLEX) {
+                const double2 v = reinterpret_cast<const double2*>(u)[idx];
+                ere[i][tx] = v.x;
+                eim[i][tx] = v.y;
+            } else {
+                ere[i][tx] = u[idx];
+            }
+        }
+    }
+    __syncthreads();
+    const int s = s0 + tx;
+    if (s >= n) return;
+    for (int i = ty; i < kTile; i += 8) {
+        const int r = r0 + i;
+        if (r >= n) break;
+        const long long idx = plane + (long long)r * n + s;
+        const long long oidx = oplane + (long long)r * n + s;
+        if (COMPLEX) {
+            const double2 v = reinterpret_cast<const double2*>(u)[idx];
+            reinterpret_cast<double2*>(out)[oidx] = make_double2(v.x - ere[tx][i], v.y - eim[tx][i]);
+        } else {
+            out[oidx] = u[idx] - ere[tx][i];
+        }
+    }
+}
+
+template <bool IN_COMPLEX, bool OUT_COMPLEX>
+__global__ void add_spin_one_body_kernel(const double* __restrict__ h, double* __restrict__ out, int l) {
+    const long long n = 2LL * l;
+    const long long total = n * n;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int P = (int)(i / n), Q = (int)(i % n);
+        double re = 0.0, im = 0.0;
+        if ((P & 1) == (Q & 1)) {
+            const long long src = (long long)(P >> 1) * l + (Q >> 1);
+            re = IN_COMPLEX ? h[2 * src] : h[src];
+            im = IN_COMPLEX ? h[2 * src + 1] : 0.0;
+        }
+        if (OUT_COMPLEX) {
+            out[2 * i] = re;
+            out[2 * i + 1] = im;
+        } else {
+            out[i] = re;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int qs_add_spin_two_body(const void* u, int in_dtype, int64_t l, void* out, int out_dtype, int anti_symmetrize,
+                                    int64_t p_begin, int64_t p_end, void* stream) {
+    QS_REQUIRE(u && out && l > 0, "qs_add_spin_two_body: bad arguments");
+    QS_REQUIRE(!(in_dtype == QS_C128 && out_dtype == QS_F64), "qs_add_spin_two_body: cannot narrow complex to real");
+    QS_REQUIRE(0 <= p_begin && p_begin <= p_end && p_end <= 2 * l, "qs_add_spin_two_body: bad plane range");
+    QS_REQUIRE(l <= 32767, "qs_add_spin_two_body: l too large");
+    if (p_begin == p_end) return QS_OK;
+    const int tiles = (int)qs_ceil_div(l, kTile);
+    const int64_t planes = p_end - p_begin;
+    const dim3 block(32, 8);
+    const double* in = static_cast<const double*>(u);
+    double* o = static_cast<double*>(out);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // gridDim.z is limited to 65535 and gridDim.y too: l <= 32767 covers y; chunk z
+    for (int64_t z0 = 0; z0 < planes; z0 += 65535) {
+        const int64_t nz = planes - z0 < 65535 ? planes - z0 : 65535;
+        const dim3 grid((unsigned)(tiles * tiles), (unsigned)l, (unsigned)nz);
+        const int64_t n = 2 * l;
+        double* oz = o + z0 * n * n * n * qs_elem_doubles(out_dtype);
+        const long long pb = p_begin + z0;
+#define QS_SPIN_LAUNCH(IC, OC)                                                                  \
+    do {                                                                                        \
+        if (anti_symmetrize)                                                                    \
+            add_spin_kernel<IC, OC, true><<<grid, block, 0, st>>>(in, oz, (int)l, tiles, pb);   \
+        else                                                                                    \
+            add_spin_kernel<IC, OC, false><<<grid, block, 0, st>>>(in, oz, (int)l, tiles, pb);  \
+    } while (0)
+        if (in_dtype == QS_C128)
+            QS_SPIN_LAUNCH(true, true);
+        else if (out_dtype == QS_C128)
+            QS_SPIN_LAUNCH(false, true);
+        else
+            QS_SPIN_LAUNCH(false, false);
+#undef QS_SPIN_LAUNCH
+        QS_LAUNCH_CHECK();
+    }
+    return QS_OK;
+}
+
+extern "C" int qs_anti_symmetrize(const void* u, int dtype, int64_t n, void* out, int64_t p_begin, int64_t p_end,
+                                  void* stream) {
+    QS_REQUIRE(u && out && n > 0 && u != out, "qs_anti_symmetrize: bad arguments (in-place is not supported)");
+    QS_REQUIRE(0 <= p_begin && p_begin <= p_end && p_end <= n, "qs_anti_symmetrize: bad plane range");
+    QS_REQUIRE(n <= 65535, "qs_anti_symmetrize: n too large");
+    if (p_begin == p_end) return QS_OK;
+    const int tiles = (int)qs_ceil_div(n, kTile);
+    const dim3 block(32, 8);
+    const dim3 grid((unsigned)(tiles * tiles), (unsigned)n, (unsigned)(p_end - p_begin));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == QS_C128)
+        antisym_kernel<true><<<grid, block, 0, st>>>(static_cast<const double*>(u), static_cast<double*>(out), (int)n,
+                                                     tiles, p_begin);
+    else
+        antisym_kernel<false><<<grid, block, 0, st>>>(static_cast<const double*>(u), static_cast<double*>(out), (int)n,
+                                                      tiles, p_begin);
+    QS_LAUNCH_CHECK();
+    return QS_OK;
+}
+
+extern "C" int qs_add_spin_one_body(const void* h, int in_dtype, int64_t l, void* out, int out_dtype, void* stream) {
+    QS_REQUIRE(h && out && l > 0, "qs_add_spin_one_body: bad arguments");
+    QS_REQUIRE(!(in_dtype == QS_C128 && out_dtype == QS_F64), "qs_add_spin_one_body: cannot narrow complex to real");
+    const long long total = 4LL * l * l;
+    long long blocks = qs_ceil_div(total, 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const double* in = static_cast<const double*>(h);
+    double* o = static_cast<double*>(out);
+    if (in_dtype == QS_C128)
+        add_spin_one_body_kernel<true, true><<<(unsigned)blocks, 256, 0, st>>>(in, o, (int)l);
+    else if (out_dtype == QS_C128)
+        add_spin_one_body_kernel<false, true><<<(unsigned)blocks, 256, 0, st>>>(in, o, (int)l);
+    else
+        add_spin_one_body_kernel<false, false><<<(unsigned)blocks, 256, 0, st>>>(in, o, (int)l);
+    QS_LAUNCH_CHECK();
+    return QS_OK;
+}

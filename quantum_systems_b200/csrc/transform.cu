@@ -1,0 +1,180 @@
+// Whole-tensor basis changes built from quarter GEMMs.
+//
+//   qs_transform_two_body : BasisSet.transform_two_body_elements (reference basis_set.py:336-350)
+//   qs_transform_one_body : BasisSet.transform_one_body_elements (reference basis_set.py:329-334)
+//
+// Four launches of the same kernel "contract the last index, store the new index slowest":
+//   u[a,b,c,d] -C-> T1[s,a,b,c] -C-> T2[r,s,a,b] -Ct^T-> T3[q,r,s,a] -Ct^T-> out[p,q,r,s]
+// which is the reference's contraction order (s, r, q, p) with every transpose folded into a store.
+#include "common.cuh"
+
+namespace {
+
+// Real tensors with an odd contracted extent cannot be described to TMA directly (row pitch must be a
+// multiple of 16 bytes), so every real (X, n) operand uses pitch P = n + (n & 1).  Intermediates are
+// written at that pitch by the producing epilogue for free; only the caller's input needs one copy.
+struct TwoBodyPlan {
+    int t_dtype;  // dtype of every intermediate and of the result
+    int64_t pitch_u, pitch_t;
+    int64_t pad_bytes, bufA_bytes, bufB_bytes, img_bytes[2], total;
+};
+
+int64_t padded_pitch(int64_t n, int dtype) { return dtype == QS_C128 ? n : n + (n & 1); }
+
+int make_plan(int64_t n, int64_t m, int u_dtype, int c_dtype, TwoBodyPlan* plan) {
+    plan->t_dtype = (u_dtype == QS_C128 || c_dtype == QS_C128) ? QS_C128 : QS_F64;
+    plan->pitch_u = padded_pitch(n, u_dtype);
+    plan->pitch_t = padded_pitch(n, plan->t_dtype);
+    const int64_t es = 8 * qs_elem_doubles(plan->t_dtype);
+    const int64_t P = plan->pitch_t;
+    const int64_t t1 = m * n * n * P, t2 = m * m * n * P, t3 = m * m * m * P;
+    plan->pad_bytes = plan->pitch_u != n ? qs_round_up(n * n * n * plan->pitch_u * 8, 1024) : 0;
+    plan->bufA_bytes = qs_round_up((t1 > t3 ? t1 : t3) * es, 1024);
+    plan->bufB_bytes = qs_round_up(t2 * es, 1024);
+    // image 0: first step, A has the dtype of u; image 1: later steps, A has t_dtype
+    int rc = qs_coeff_image_bytes(n, m, u_dtype, c_dtype, &plan->img_bytes[0]);
+    if (rc) return rc;
+    rc = qs_coeff_image_bytes(n, m, plan->t_dtype, c_dtype, &plan->img_bytes[1]);
+    if (rc) return rc;
+    plan->img_bytes[0] = qs_round_up(plan->img_bytes[0], 1024);
+    plan->img_bytes[1] = qs_round_up(plan->img_bytes[1], 1024);
+    // images: [C for step 1][C for step 2][Ct^T for steps 3, 4]
+    plan->total = plan->pad_bytes + plan->bufA_bytes + plan->bufB_bytes + plan->img_bytes[0] + 2 * plan->img_bytes[1];
+    return QS_OK;
+}
+
+__global__ void pad_rows_kernel(const double* __restrict__ in, double* __restrict__ out, long long rows, int n,
+                                int pitch) {
+    const long long total = rows * pitch;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / pitch;
+        const int c = (int)(i - r * pitch);
+        out[i] = c < n ? in[r * n + c] : 0.0;
+    }
+}
+
+int pad_rows(const void* in, void* out, int64_t rows, int64_t n, int64_t pitch, void* stream) {
+    const long long total = rows * pitch;
+    long long blocks = qs_ceil_div(total, 256);
+    const long long cap = (long long)qs_sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    pad_rows_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const double*>(in), static_cast<double*>(out), rows, (int)n, (int)pitch);
+    QS_LAUNCH_CHECK();
+    return QS_OK;
+}
+
+// Contract the last index of A (rows X, extent K, pitch lda) and store the new index slowest; the
+// remaining row index x = (x_hi, x_lo) with x_lo < lo_extent is written at x_hi * lo_pitch + x_lo.
+int rotated_quarter(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda, const void* image, int m_dtype,
+                    int64_t W, void* out, int64_t lo_extent, int64_t lo_pitch, void* stream) {
+    const int64_t plane = X / lo_extent * lo_pitch;
+    return qs_quarter_transform(A, a_dtype, X, K, lda, image, m_dtype, W, out, lo_extent, 1, lo_pitch, 1, 0, plane,
+                                stream);
+}
+
+}  // namespace
+
+extern "C" int qs_transform_two_body_workspace_bytes(int64_t n, int64_t n_new, int u_dtype, int c_dtype,
+                                                     int64_t* bytes) {
+    QS_REQUIRE(n > 0 && n_new > 0 && bytes, "qs_transform_two_body_workspace_bytes: bad arguments");
+    TwoBodyPlan plan;
+    int rc = make_plan(n, n_new, u_dtype, c_dtype, &plan);
+    if (rc) return rc;
+    *bytes = plan.total;
+    return QS_OK;
+}
+
+extern "C" int qs_transform_two_body(const void* u, int u_dtype, const void* C, const void* Ct, int c_dtype, int64_t n,
+                                     int64_t n_new, void* out, void* workspace, int64_t workspace_bytes,
+                                     void* stream) {
+    QS_REQUIRE(u && C && out && workspace, "qs_transform_two_body: null pointer");
+    QS_REQUIRE(n > 0 && n_new > 0, "qs_transform_two_body: bad extents");
+    TwoBodyPlan plan;
+    int rc = make_plan(n, n_new, u_dtype, c_dtype, &plan);
+    if (rc) return rc;
+    QS_REQUIRE(workspace_bytes >= plan.total, "qs_transform_two_body: workspace too small (%lld < %lld)",
+               (long long)workspace_bytes, (long long)plan.total);
+    QS_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0,
+               "qs_transform_two_body: workspace must be 1 KiB aligned");
+    const int64_t N = n, M = n_new, P = plan.pitch_t;
+    char* ws = static_cast<char*>(workspace);
+    void* padded = ws;
+    void* bufA = ws + plan.pad_bytes;
+    void* bufB = static_cast<char*>(bufA) + plan.bufA_bytes;
+    void* img1 = static_cast<char*>(bufB) + plan.bufB_bytes;
+    void* img2 = static_cast<char*>(img1) + plan.img_bytes[0];
+    void* img3 = static_cast<char*>(img2) + plan.img_bytes[1];
+    const int td = plan.t_dtype;
+
+    // M[k, w] = C[k, w] (row-major n x m) for steps 1-2
+    if ((rc = qs_build_coeff_image(C, c_dtype, M, 1, 0, N, M, u_dtype, img1, stream))) return rc;
+    if ((rc = qs_build_coeff_image(C, c_dtype, M, 1, 0, N, M, td, img2, stream))) return rc;
+    // M[k, w] = Ct[w, k] for steps 3-4; Ct (m x n row-major), or conj(C)^T -> conj(C[k, w])
+    if (Ct) {
+        if ((rc = qs_build_coeff_image(Ct, c_dtype, 1, N, 0, N, M, td, img3, stream))) return rc;
+    } else {
+        if ((rc = qs_build_coeff_image(C, c_dtype, M, 1, 1, N, M, td, img3, stream))) return rc;
+    }
+    const void* a0 = u;
+    if (plan.pad_bytes) {
+        if ((rc = pad_rows(u, padded, N * N * N, N, plan.pitch_u, stream))) return rc;
+        a0 = padded;
+    }
+    // T1[s,a,b,c] ; T2[r,s,a,b] ; T3[q,r,s,a] (last axis at pitch P) ; out[p,q,r,s] dense
+    if ((rc = rotated_quarter(a0, u_dtype, N * N * N, N, plan.pitch_u, img1, c_dtype, M, bufA, N, P, stream))) return rc;
+    if ((rc = rotated_quarter(bufA, td, M * N * N, N, P, img2, c_dtype, M, bufB, N, P, stream))) return rc;
+    if ((rc = rotated_quarter(bufB, td, M * M * N, N, P, img3, c_dtype, M, bufA, N, P, stream))) return rc;
+    if ((rc = rotated_quarter(bufA, td, M * M * M, N, P, img3, c_dtype, M, out, M, M, stream))) return rc;
+    return QS_OK;
+}
+
+extern "C" int qs_transform_one_body_workspace_bytes(int64_t n, int64_t n_new, int h_dtype, int c_dtype,
+                                                     int64_t* bytes) {
+    QS_REQUIRE(n > 0 && n_new > 0 && bytes, "qs_transform_one_body_workspace_bytes: bad arguments");
+    const int td = (h_dtype == QS_C128 || c_dtype == QS_C128) ? QS_C128 : QS_F64;
+    int64_t img_a, img_b;
+    int rc;
+    if ((rc = qs_coeff_image_bytes(n, n_new, h_dtype, c_dtype, &img_a))) return rc;
+    if ((rc = qs_coeff_image_bytes(n, n_new, td, c_dtype, &img_b))) return rc;
+    const int64_t ph = padded_pitch(n, h_dtype), pt = padded_pitch(n, td);
+    *bytes = qs_round_up(n * ph * 8, 1024) + qs_round_up(n_new * pt * 8 * qs_elem_doubles(td), 1024) +
+             qs_round_up(img_a, 1024) + qs_round_up(img_b, 1024);
+    return QS_OK;
+}
+
+extern "C" int qs_transform_one_body(const void* h, int h_dtype, const void* C, const void* Ct, int c_dtype, int64_t n,
+                                     int64_t n_new, void* out, void* workspace, void* stream) {
+    // out[p,q] = sum_ab Ct[p,a] h[a,b] C[b,q] with the same rotated-store kernel:
+    //   step 1: T[q, a]   = sum_b h[a, b] C[b, q]     (contract last, new index slowest)
+    //   step 2: out[p, q] = sum_a T[q, a] Ct[p, a]    (contract last, new index slowest)
+    QS_REQUIRE(h && C && out && workspace, "qs_transform_one_body: null pointer");
+    QS_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0,
+               "qs_transform_one_body: workspace must be 1 KiB aligned");
+    const int td = (h_dtype == QS_C128 || c_dtype == QS_C128) ? QS_C128 : QS_F64;
+    int64_t img_a, img_b;
+    int rc;
+    if ((rc = qs_coeff_image_bytes(n, n_new, h_dtype, c_dtype, &img_a))) return rc;
+    if ((rc = qs_coeff_image_bytes(n, n_new, td, c_dtype, &img_b))) return rc;
+    const int64_t ph = padded_pitch(n, h_dtype), pt = padded_pitch(n, td);
+    char* ws = static_cast<char*>(workspace);
+    void* hpad = ws;
+    void* T = ws + qs_round_up(n * ph * 8, 1024);
+    void* img1 = static_cast<char*>(T) + qs_round_up(n_new * pt * 8 * qs_elem_doubles(td), 1024);
+    void* img2 = static_cast<char*>(img1) + qs_round_up(img_a, 1024);
+    if ((rc = qs_build_coeff_image(C, c_dtype, n_new, 1, 0, n, n_new, h_dtype, img1, stream))) return rc;
+    if (Ct) {
+        if ((rc = qs_build_coeff_image(Ct, c_dtype, 1, n, 0, n, n_new, td, img2, stream))) return rc;
+    } else {
+        if ((rc = qs_build_coeff_image(C, c_dtype, n_new, 1, 1, n, n_new, td, img2, stream))) return rc;
+    }
+    const void* a0 = h;
+    if (ph != n) {
+        if ((rc = pad_rows(h, hpad, n, n, ph, stream))) return rc;
+        a0 = hpad;
+    }
+    if ((rc = rotated_quarter(a0, h_dtype, n, n, ph, img1, c_dtype, n_new, T, n, pt, stream))) return rc;
+    if ((rc = rotated_quarter(T, td, n_new, n, pt, img2, c_dtype, n_new, out, n_new, n_new, stream))) return rc;
+    return QS_OK;
+}

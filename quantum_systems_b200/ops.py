@@ -1,0 +1,235 @@
+"""Tensor-level operators of the hot path: torch CUDA tensors in, torch CUDA tensors out.
+
+Each function validates shapes/dtypes on the host, allocates the result and the scratch through
+torch's caching allocator, and enqueues hand-written sm_100a kernels from ``libqsb200.so`` on the
+current CUDA stream through the C ABI (``include/qsb200.h``).  torch performs no arithmetic here.
+There is no CPU path: a CPU tensor, a missing library or a failing kernel raises.
+"""
+
+import ctypes
+
+import torch
+
+from . import _native
+from ._native import QS_C128, QS_F64
+
+_DTYPES = {torch.float64: QS_F64, torch.complex128: QS_C128}
+
+
+def _code(t):
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise TypeError(f"quantum_systems_b200 computes in float64/complex128 only, got {t.dtype}") from None
+
+
+def _device_tensor(t, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor on a CUDA device, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} lives on {t.device}: quantum_systems_b200 has no CPU fallback")
+    _code(t)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _workspace(nbytes, device):
+    """Scratch from the caching allocator, aligned to 1 KiB.  Returns (owner tensor, pointer)."""
+    buf = torch.empty(int(nbytes) + 1024, dtype=torch.uint8, device=device)
+    base = buf.data_ptr()
+    aligned = (base + 1023) & ~1023
+    return buf, ctypes.c_void_p(aligned)
+
+
+def _result_dtype(*tensors):
+    return torch.complex128 if any(t.dtype == torch.complex128 for t in tensors) else torch.float64
+
+
+def _coefficients(C, C_tilde):
+    """Bring C (n, n_new) and the optional C_tilde (n_new, n) to one dtype."""
+    C = _device_tensor(C, "C")
+    if C.dim() != 2:
+        raise ValueError("C must be a matrix (n, n_new)")
+    if C_tilde is not None:
+        C_tilde = _device_tensor(C_tilde, "C_tilde")
+        if tuple(C_tilde.shape) != (C.shape[1], C.shape[0]):
+            raise ValueError(f"C_tilde must have shape {(C.shape[1], C.shape[0])}, got {tuple(C_tilde.shape)}")
+        dt = _result_dtype(C, C_tilde)
+        C, C_tilde = C.to(dt), C_tilde.to(dt)
+    return C, C_tilde
+
+
+def transform_two_body(u, C, C_tilde=None):
+    """``u'_pqrs = sum C~[p,a] C~[q,b] u[a,b,c,d] C[c,r] C[d,s]`` (reference basis_set.py:336-350)."""
+    u = _device_tensor(u, "u")
+    C, C_tilde = _coefficients(C, C_tilde)
+    n, m = C.shape
+    if tuple(u.shape) != (n, n, n, n):
+        raise ValueError(f"u must have shape {(n,) * 4} to be contracted with C {tuple(C.shape)}, got {tuple(u.shape)}")
+    out = torch.empty((m, m, m, m), dtype=_result_dtype(u, C), device=u.device)
+    nbytes = ctypes.c_int64(0)
+    _native.call("qs_transform_two_body_workspace_bytes", n, m, _code(u), _code(C), ctypes.byref(nbytes))
+    owner, ws = _workspace(nbytes.value, u.device)
+    _native.call(
+        "qs_transform_two_body", _ptr(u), _code(u), _ptr(C), _ptr(C_tilde), _code(C), n, m, _ptr(out), ws,
+        nbytes.value, _stream(),
+    )
+    owner.record_stream(torch.cuda.current_stream())
+    return out
+
+
+def transform_one_body(h, C, C_tilde=None):
+    """``C~ (h C)`` (reference basis_set.py:329-334)."""
+    h = _device_tensor(h, "h")
+    C, C_tilde = _coefficients(C, C_tilde)
+    n, m = C.shape
+    if tuple(h.shape) != (n, n):
+        raise ValueError(f"h must have shape {(n, n)}, got {tuple(h.shape)}")
+    out = torch.empty((m, m), dtype=_result_dtype(h, C), device=h.device)
+    nbytes = ctypes.c_int64(0)
+    _native.call("qs_transform_one_body_workspace_bytes", n, m, _code(h), _code(C), ctypes.byref(nbytes))
+    owner, ws = _workspace(nbytes.value, h.device)
+    _native.call(
+        "qs_transform_one_body", _ptr(h), _code(h), _ptr(C), _ptr(C_tilde), _code(C), n, m, _ptr(out), ws, _stream()
+    )
+    owner.record_stream(torch.cuda.current_stream())
+    return out
+
+
+def coeff_image(M, K, W, a_dtype, stride_k, stride_w, conj=False):
+    """Fragment-ordered image of ``M[k, w] = M.flat[k*stride_k + w*stride_w]`` for quarter_transform."""
+    M = _device_tensor(M, "M")
+    a_code = _DTYPES[a_dtype]
+    nbytes = ctypes.c_int64(0)
+    _native.call("qs_coeff_image_bytes", K, W, a_code, _code(M), ctypes.byref(nbytes))
+    image = torch.empty(nbytes.value // 8, dtype=torch.float64, device=M.device)
+    _native.call(
+        "qs_build_coeff_image", _ptr(M), _code(M), stride_k, stride_w, int(bool(conj)), K, W, a_code, _ptr(image),
+        _stream(),
+    )
+    return image
+
+
+def quarter_transform(A, X, K, lda, image, m_dtype, W, out, x_inner, sx0, sx1, w_inner, sw0, sw1):
+    """One contraction ``sum_k A[x,k] M[k,w]`` with the 2-level strided store (see include/qsb200.h)."""
+    A = _device_tensor(A, "A")
+    _native.call(
+        "qs_quarter_transform", _ptr(A), _code(A), X, K, lda, _ptr(image), _DTYPES[m_dtype], W, _ptr(out), x_inner,
+        sx0, sx1, w_inner, sw0, sw1, _stream(),
+    )
+    return out
+
+
+def add_spin_two_body(u, anti_symmetrize=False, out_dtype=None, planes=None, out=None):
+    """Spin-double ``u`` (l,l,l,l) -> (2l,2l,2l,2l), optionally fused with the anti-symmetrisation
+    and the widening cast (reference basis_set.py:772-778, :298-319).  ``planes=(P0, P1)`` restricts
+    the leading spin-orbital index (multi-GPU shard); the result then has ``P1 - P0`` leading planes."""
+    u = _device_tensor(u, "u")
+    l = u.shape[0]
+    if tuple(u.shape) != (l, l, l, l):
+        raise ValueError(f"u must be (l,l,l,l), got {tuple(u.shape)}")
+    out_dtype = u.dtype if out_dtype is None else out_dtype
+    p0, p1 = (0, 2 * l) if planes is None else planes
+    if out is None:
+        out = torch.empty((p1 - p0, 2 * l, 2 * l, 2 * l), dtype=out_dtype, device=u.device)
+    _native.call(
+        "qs_add_spin_two_body", _ptr(u), _code(u), l, _ptr(out), _DTYPES[out_dtype], int(bool(anti_symmetrize)), p0,
+        p1, _stream(),
+    )
+    return out
+
+
+def anti_symmetrize(u):
+    """``u - u.transpose(0,1,3,2)`` (reference basis_set.py:776-778); returns a new tensor."""
+    u = _device_tensor(u, "u")
+    n = u.shape[-1]
+    if u.dim() != 4 or tuple(u.shape[1:]) != (n, n, n):
+        raise ValueError(f"u must be (planes,n,n,n), got {tuple(u.shape)}")
+    out = torch.empty_like(u)
+    # `u` may be a leading-index shard: planes [0, u.shape[0]) of the local block
+    _native.call("qs_anti_symmetrize", _ptr(u), _code(u), n, _ptr(out), 0, u.shape[0], _stream())
+    return out
+
+
+def add_spin_one_body(h, out_dtype=None):
+    """``kron(h, I_2)`` (reference basis_set.py:768-770)."""
+    h = _device_tensor(h, "h")
+    l = h.shape[0]
+    if tuple(h.shape) != (l, l):
+        raise ValueError(f"h must be square, got {tuple(h.shape)}")
+    out_dtype = h.dtype if out_dtype is None else out_dtype
+    out = torch.empty((2 * l, 2 * l), dtype=out_dtype, device=h.device)
+    _native.call("qs_add_spin_one_body", _ptr(h), _code(h), l, _ptr(out), _DTYPES[out_dtype], _stream())
+    return out
+
+
+def _fock(name, h, u, n_occ, f):
+    h = _device_tensor(h, "h")
+    u = _device_tensor(u, "u")
+    n = h.shape[0]
+    if tuple(h.shape) != (n, n) or tuple(u.shape) != (n, n, n, n):
+        raise ValueError(f"h must be (n,n) and u (n,n,n,n), got {tuple(h.shape)} and {tuple(u.shape)}")
+    if f is None:
+        f = torch.empty_like(h)
+    else:
+        if not (isinstance(f, torch.Tensor) and f.is_cuda and f.is_contiguous()):
+            raise RuntimeError("f must be a contiguous CUDA tensor to be filled in place")
+        if f.shape != h.shape or f.dtype != h.dtype:
+            raise ValueError("f must have the shape and dtype of h")
+    _native.call(name, _ptr(h), _code(h), _ptr(u), _code(u), n, int(n_occ), _ptr(f), 0, n, _stream())
+    return f
+
+
+def fock_general(h, u, n_occ, f=None):
+    """``f = h + sum_i u[p,i,q,i]`` (reference general_orbital_system.py:119-159); ``f`` filled in place."""
+    return _fock("qs_fock_general", h, u, n_occ, f)
+
+
+def fock_spatial(h, u, n_occ, f=None):
+    """``f = h + 2 u[p,i,q,i] - u[p,i,i,q]`` (reference spatial_orbital_system.py:150-190)."""
+    return _fock("qs_fock_spatial", h, u, n_occ, f)
+
+
+def odqd_coulomb(C, inner_grid, alpha, a):
+    """Grid Coulomb elements ``u_abcd`` of the 1-D quantum dot (reference one_dim_qd.py:275-280).
+    ``C``: (G', l) eigenvectors on the interior grid; ``inner_grid``: (G',)."""
+    C = _device_tensor(C, "C")
+    inner_grid = _device_tensor(inner_grid, "inner_grid")
+    if C.dtype != torch.float64 or inner_grid.dtype != torch.float64:
+        raise TypeError("the ODQD grid build is real float64")
+    Gp, l = C.shape
+    if tuple(inner_grid.shape) != (Gp,):
+        raise ValueError("inner_grid must have one entry per row of C")
+    out = torch.empty((l, l, l, l), dtype=torch.float64, device=C.device)
+    nbytes = ctypes.c_int64(0)
+    _native.call("qs_odqd_coulomb_workspace_bytes", l, Gp, ctypes.byref(nbytes))
+    owner, ws = _workspace(nbytes.value, C.device)
+    _native.call(
+        "qs_odqd_coulomb", _ptr(C), _ptr(inner_grid), float(alpha), float(a), l, Gp, _ptr(out), ws, nbytes.value,
+        _stream(),
+    )
+    owner.record_stream(torch.cuda.current_stream())
+    return out
+
+
+def probe_dmma_tflops():
+    """Measured FP64 tensor-pipe peak (register-resident DMMA.8x8x4 loop) in TFLOP/s."""
+    val = ctypes.c_double(0.0)
+    _native.call("qs_probe_dmma_tflops", ctypes.byref(val), _stream())
+    return val.value
+
+
+def probe_copy_gbs(nbytes=1 << 32):
+    """Measured streaming-copy bandwidth in GB/s (read + write bytes)."""
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    scratch.zero_()
+    val = ctypes.c_double(0.0)
+    _native.call("qs_probe_copy_gbs", ctypes.byref(val), _ptr(scratch), nbytes, _stream())
+    return val.value
