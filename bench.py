@@ -1,0 +1,426 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: ``change_basis`` (four-index transform + one-body) in FP64.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One *step* = one ``BasisSet.change_basis(C)`` pass over one synthetic basis set.
+
+* N = 1: BASELINE.json ``configs[1]`` -- synthetic real FP64 ``BasisSet`` with l = 128, random
+  orthonormal C.
+* N > 1 (torchrun, one rank per GPU): ONE tensor sharded on its leading index across the ranks,
+  re-partitioned by one all-to-all between the second and third quarter transforms; n grows as
+  ``128 * N**(1/5)`` (148 / 168 / 192 at N = 2 / 4 / 8) so the flops per GPU stay fixed: weak scaling.
+
+Printed JSON line (rank 0): ``value`` = whole-job TFLOP/s with inputs resident in HBM, device-timed
+with CUDA events (max over ranks); ``e2e`` = the same metric through the public API with HOST
+(numpy, pinned) arrays -- H2D of u/h/s/C and D2H of the results inside the timed region;
+``roofline`` = the dominant kernel (FP64 DMMA quarter GEMM) timed live with CUDA events on its
+launching stream inside the timed region; ``cpu_baseline`` = the numpy oracle (the reference's own
+call sequence, oracle/qs_oracle.py) on the box's host cores.
+
+``--impl reference`` times that CPU path alone (the reference is pure Python over numpy; the oracle
+issues the same numpy calls in the same order), all host threads, one bounded sample per step.
+"""
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "change_basis FP64 TFLOP/s"
+UNIT = "TFLOP/s"
+N_BY_GPUS = {1: 128, 2: 148, 4: 168, 8: 192}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=0, help="override the number of orbitals (development)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def transform_flops(n, m=None):
+    """Real flops of change_basis on (h, s, u): SURVEY.md section 8d."""
+    m = n if m is None else m
+    two_body = 2.0 * (n**4 * m + n**3 * m**2 + n**2 * m**3 + n * m**4)
+    one_body = 2 * 2.0 * (n * n * m + n * m * m)  # h and s
+    return two_body + one_body
+
+
+def workload_n(args):
+    if args.n:
+        return args.n
+    return N_BY_GPUS.get(args.gpus, int(round(128 * args.gpus**0.2 / args.gpus)) * args.gpus)
+
+
+def make_inputs(n, seed=2):
+    """configs[1] inputs on the host: u ~ N(0,1) with u_pqrs = u_qpsr, symmetric h,
+    s = I, C = qr(N(0,1))."""
+    import numpy as np
+
+    rng = np.random.default_rng(seed)
+    u = rng.standard_normal((n, n, n, n))
+    u = 0.5 * (u + u.transpose(1, 0, 3, 2))
+    h = rng.standard_normal((n, n))
+    h = 0.5 * (h + h.T)
+    s = np.eye(n)
+    C = np.linalg.qr(rng.standard_normal((n, n)))[0]
+    return {"u": u, "h": h, "s": s, "C": np.ascontiguousarray(C)}
+
+
+def host_threads():
+    try:
+        from threadpoolctl import threadpool_info
+
+        blas = [p["num_threads"] for p in threadpool_info() if p.get("user_api") == "blas"]
+        if blas:
+            return max(blas)
+    except Exception:
+        pass
+    return os.cpu_count() or 1
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU path (oracle = the reference's numpy call sequence); used by cpu_baseline and --impl reference
+# ------------------------------------------------------------------------------------------------
+def cpu_change_basis_seconds(inputs):
+    from oracle import qs_oracle as oracle
+
+    t0 = time.perf_counter()
+    out = oracle.change_basis({"h": inputs["h"], "s": inputs["s"], "u": inputs["u"]}, inputs["C"])
+    dt = time.perf_counter() - t0
+    return dt, out
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # rank 0 alone runs the CPU arm
+    total = args.steps + args.warmup
+    n_full = workload_n(args)
+    # bound the run to a few minutes: probe at n = 64, extrapolate ~ n^5, shrink the sample if needed
+    probe, _ = cpu_change_basis_seconds(make_inputs(64, seed=3))
+    n = n_full
+    while n > 64 and probe * (n / 64.0) ** 5 * total > 150.0:
+        n -= 16
+    inputs = make_inputs(n)
+    for _ in range(args.warmup):
+        cpu_change_basis_seconds(inputs)
+    times = [cpu_change_basis_seconds(inputs)[0] for _ in range(args.steps)]
+    sec = sum(times) / len(times)
+    value = transform_flops(n) / sec * 1e-12
+    sample = (
+        f"full workload n={n}" if n == n_full else f"n={n} sample of the n={n_full} workload (throughput metric, "
+        f"bounded so {total} steps end within minutes)"
+    ) + "; oracle.change_basis = reference numpy call sequence (h, s, u)"
+    line = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": value,
+        "unit": UNIT,
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": sec * 1e3,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args.gpus, n_full), "n": n_full, "n_timed": n},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": host_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(gpus, n):
+    if gpus == 1:
+        return f"configs[1]: synthetic real FP64 BasisSet l={n}, random orthonormal C, change_basis on 1xB200"
+    return (
+        f"configs[1] scaled to {gpus} GPUs: real FP64 BasisSet l={n} (n ~ 128*N^(1/5), equal flops per GPU), u sharded "
+        "on its leading index, one all-to-all per change_basis"
+    )
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = (
+        "clocks.sm,clocks.max.sm,power.draw,utilization.gpu,clocks_event_reasons.hw_slowdown,"
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+        "clocks_event_reasons.sw_power_cap"
+    )
+    REASONS = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+    def __init__(self, index):
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "50"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, sm_max, power, reasons = [], [], [], set()
+        for row in out.strip().splitlines():
+            cols = [c.strip() for c in row.split(",")]
+            if len(cols) < 8:
+                continue
+            try:
+                clock, clock_max, watts, util = float(cols[0]), float(cols[1]), float(cols[2]), float(cols[3])
+            except ValueError:
+                continue
+            sm_max.append(clock_max)
+            if util > 0 or watts > 300:
+                sm.append(clock)
+                power.append(watts)
+                for name, flag in zip(self.REASONS, cols[4:8]):
+                    if flag == "Active":
+                        reasons.add(name)
+        return {
+            "sm_mhz": statistics.median(sm) if sm else None,
+            "sm_max_mhz": max(sm_max) if sm_max else None,
+            "reasons": sorted(reasons),
+            "samples": len(sm),
+            "power_w_max": max(power) if power else None,
+        }
+
+
+# ------------------------------------------------------------------------------------------------
+# the B200 arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from quantum_systems_b200 import BasisSet, _native, ops, xp
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: quantum_systems_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = _native.load()
+    n = workload_n(args)
+    flops = transform_flops(n)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    inputs = make_inputs(n)
+    peak_tflops = ops.probe_dmma_tflops()
+
+    # ---- leg 1: inputs resident in HBM -----------------------------------------------------------
+    if world == 1:
+        basis = BasisSet(n, 1, np=xp)
+        basis.h, basis.s, basis.u = inputs["h"], inputs["s"], inputs["u"]
+        C_dev = xp.asarray(inputs["C"])
+
+        def step():
+            basis.change_basis(C_dev)
+    else:
+        from quantum_systems_b200 import sharded
+
+        basis = sharded.ShardedBasisSet.from_global(n, inputs["h"], inputs["s"], inputs["u"], rank, world)
+        C_dev = xp.asarray(inputs["C"])
+
+        def step():
+            basis.change_basis(C_dev)
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    lib.qs_kernel_timing_enable(1)
+    launches0 = lib.qs_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    launches = lib.qs_launch_count() - launches0
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    # dominant kernel: the quarter GEMM, timed by events around its own launches inside the region
+    import ctypes
+
+    k_ms, k_work, k_spans = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
+    _native.call("qs_kernel_timing_read", 0, ctypes.byref(k_ms), ctypes.byref(k_work), ctypes.byref(k_spans))
+    lib.qs_kernel_timing_enable(0)
+    ms_per_step = ms / args.steps
+    value = flops / (ms_per_step * 1e-3) * 1e-12
+
+    # ---- leg 2: end to end through the public API with host arrays -------------------------------
+    e2e = None
+    if not args.no_e2e and world == 1:
+        def pinned(a):
+            t = torch.empty(a.shape, dtype=torch.float64, pin_memory=True)
+            t.numpy()[...] = a
+            return t.numpy()
+
+        host_basis = BasisSet(n, 1, np=np)
+        host_basis.h, host_basis.s, host_basis.u = pinned(inputs["h"]), pinned(inputs["s"]), pinned(inputs["u"])
+        C_host = pinned(inputs["C"])
+        h2d = sum(a.nbytes for a in (host_basis.h, host_basis.s, host_basis.u, C_host))
+        e2e_steps = min(args.steps, 10)
+        for _ in range(max(args.warmup, 3)):
+            host_basis.change_basis(C_host)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            host_basis.change_basis(C_host)
+            assert isinstance(host_basis.u, np.ndarray)  # the result is back on the host
+        torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        d2h = sum(a.nbytes for a in (host_basis.h, host_basis.s, host_basis.u))
+        e2e = {
+            "value": flops / e2e_s * 1e-12, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+            "api": "BasisSet(np=numpy).change_basis(C) on pinned host ndarrays",
+        }
+        del host_basis
+    elif world > 1 and not args.no_e2e:
+        e2e = basis.e2e_leg(inputs, args, flops) if hasattr(basis, "e2e_leg") else None
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------------
+    achieved = k_work.value / (k_ms.value * 1e-3) * 1e-12 if k_ms.value > 0 else None
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "quarter_gemm_traffic.json")
+    if os.path.exists(prof):
+        with open(prof) as fh:
+            traffic = json.load(fh).get(f"n{n}", {}).get("dram_bytes_per_launch")
+    roofline = {
+        "kernel": "quarter_gemm_kernel (FP64 DMMA.8x8x4 + TMA)",
+        "bound": "tensor",
+        "achieved": achieved,
+        "peak": peak_tflops,
+        "unit": "TFLOP/s",
+        "frac": achieved / peak_tflops if achieved else None,
+        "traffic": traffic,
+        "peak_source": "FP64 tensor pipe measured in this run by a register-resident DMMA.8x8x4 loop "
+        "(qs_probe_dmma_tflops); MEASURED_PEAKS.json holds only bf16 and HBM-copy figures",
+        "launches_timed": int(k_spans.value),
+        "kernel_share_of_step": k_ms.value / ms if ms > 0 else None,
+        "algorithmic_flops_per_launch": k_work.value / max(int(k_spans.value), 1),
+        "algorithmic_bytes_per_launch": 2.0 * 8 * n**4,
+        "hbm_gbs_at_achieved": (2.0 * 8 * n**4 * int(k_spans.value)) / (k_ms.value * 1e-3) * 1e-9 if k_ms.value > 0 else None,
+        "hbm_peak_gbs_measured": _measured_peaks().get("hbm_gbs"),
+    }
+
+    # ---- CPU baseline (numpy oracle on this box's host cores) ------------------------------------
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        sec, ref_out = cpu_change_basis_seconds(inputs)
+        cpu_baseline = {
+            "value": transform_flops(n) / sec * 1e-12, "unit": UNIT, "cores": host_threads(), "kind": "port",
+            "seconds": sec,
+            "sample": f"full workload once: oracle.change_basis (reference numpy call sequence) on the same n={n} inputs",
+        }
+        # the timed GPU path and the CPU path agree on this very input (north-star tolerance)
+        check = BasisSet(n, 1, np=xp)
+        check.h, check.s, check.u = inputs["h"], inputs["s"], inputs["u"]
+        check.change_basis(C_dev)
+        err = float(np.abs(check.u.cpu().numpy() - ref_out["u"]).max()) / float(np.abs(ref_out["u"]).max())
+        cpu_baseline["max_rel_err_vs_gpu"] = err
+        assert err <= 1e-12, f"GPU change_basis deviates from the CPU oracle: {err:.3e}"
+
+    line = {
+        "metric": METRIC,
+        "value": value,
+        "unit": UNIT,
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": ms_per_step,
+        "wall_s_per_change_basis": ms_per_step * 1e-3,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f64",
+        "data": "synthetic",
+        "config": {
+            "workload": workload_name(world, n),
+            "n": n,
+            "flops_per_step": flops,
+            "l2": "inputs (8*n^4 bytes per tensor pass) exceed the 126 MB L2; no explicit flush",
+        },
+        "e2e": e2e,
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return json.load(fh)
+    except OSError:
+        return {}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -103,6 +103,15 @@ int qs_anti_symmetrize(const void* u, int dtype, int64_t n, void* out, int64_t p
 int qs_add_spin_one_body(const void* h, int in_dtype, int64_t l, void* out, int out_dtype,
                          void* stream);
 
+/* Two-body part of S^2 from the three (n, n) complex128 spin matrices S_x, S_y, S_z:
+ *   out[p,q,r,s] = sum_i S_i[p,r] S_i[q,s]  (- sum_i S_i[p,s] S_i[q,r] if anti_symmetrize)
+ * replaces the einsum loop of BasisSet.setup_spin_squared_operator (basis_set.py:743-747) and, applied
+ * to basis-changed factors C~ S_i C, the second O(n^5) transform of _change_basis_two_body_elements
+ * (:379-382).  Planes p in [p_begin, p_end) are written to `out` (complex128). */
+int qs_spin_squared_two_body(const void* sx, const void* sy, const void* sz, int64_t n,
+                             int anti_symmetrize, void* out, int64_t p_begin, int64_t p_end,
+                             void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Fock matrices (warp-shuffle reductions over the occupied index).
  *   general : f[p,q] = h[p,q] + sum_{i<n_occ} u[p,i,q,i]                    general_orbital_system.py:119-159
@@ -114,6 +123,12 @@ int qs_fock_general(const void* h, int h_dtype, const void* u, int u_dtype, int6
                     int64_t n_occ, void* f, int64_t p_begin, int64_t p_end, void* stream);
 int qs_fock_spatial(const void* h, int h_dtype, const void* u, int u_dtype, int64_t n,
                     int64_t n_occ, void* f, int64_t p_begin, int64_t p_end, void* stream);
+/* Same reductions on pre-gathered (n_occ, n, n) blocks direct[i,p,q] = u[p,i,q,i] and (optional,
+ * may be NULL) exchange[i,p,q] = u[p,i,i,q]:  f = h + scale_direct * sum_i direct + scale_exchange *
+ * sum_i exchange.  Used when u lives in host memory and only the needed elements are staged. */
+int qs_fock_gathered(const void* h, int h_dtype, const void* direct, const void* exchange,
+                     int u_dtype, int64_t n, int64_t n_occ, double scale_direct,
+                     double scale_exchange, void* f, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * ODQD grid Coulomb build  u_abcd = sum_pq C_pa C_qb C_pc C_qd alpha/sqrt((x_p-x_q)^2 + a^2)
@@ -127,6 +142,22 @@ int qs_odqd_coulomb_workspace_bytes(int64_t l, int64_t Gp, int64_t* bytes);
 int qs_odqd_coulomb(const double* Cmat, const double* grid, double alpha, double a, int64_t l,
                     int64_t Gp, double* u_out, void* workspace, int64_t workspace_bytes,
                     void* stream);
+
+/* Instrumentation for the benchmark harness.
+ *   qs_launch_count        : kernels launched by this library since it was loaded (process-wide).
+ *   qs_kernel_timing_enable: 1 = bracket every launch site of a kernel family with CUDA events on
+ *                            the launching stream (cleared on every call); 0 = off (default).
+ *   qs_kernel_timing_read  : synchronise and sum the recorded spans of one family: device
+ *                            milliseconds, algorithmic work (flops for QS_FAMILY_QUARTER_GEMM, bytes
+ *                            for QS_FAMILY_SPIN_PASS) and the number of spans. */
+#define QS_FAMILY_QUARTER_GEMM 0
+#define QS_FAMILY_SPIN_PASS 1
+#define QS_FAMILY_FOCK 2
+#define QS_FAMILY_EXCHANGE 3
+int64_t qs_launch_count(void);
+int qs_kernel_timing_enable(int enable);
+int qs_kernel_timing_read(int family, double* host_ms_total, double* host_work_total,
+                          int64_t* host_spans);
 
 /* Roofline denominators measured in place: register-resident DMMA.8x8x4 loop (FP64 tensor pipe)
  * and a streaming copy.  Host out-pointers. */

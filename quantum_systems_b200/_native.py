@@ -34,10 +34,15 @@ SIGNATURES = {
     "qs_add_spin_two_body": [_ptr, _int, _i64, _ptr, _int, _int, _i64, _i64, _ptr],
     "qs_anti_symmetrize": [_ptr, _int, _i64, _ptr, _i64, _i64, _ptr],
     "qs_add_spin_one_body": [_ptr, _int, _i64, _ptr, _int, _ptr],
+    "qs_spin_squared_two_body": [_ptr, _ptr, _ptr, _i64, _int, _ptr, _i64, _i64, _ptr],
+    "qs_fock_gathered": [_ptr, _int, _ptr, _ptr, _int, _i64, _i64, _dbl, _dbl, _ptr, _ptr],
     "qs_fock_general": [_ptr, _int, _ptr, _int, _i64, _i64, _ptr, _i64, _i64, _ptr],
     "qs_fock_spatial": [_ptr, _int, _ptr, _int, _i64, _i64, _ptr, _i64, _i64, _ptr],
     "qs_odqd_coulomb_workspace_bytes": [_i64, _i64, ctypes.POINTER(_i64)],
     "qs_odqd_coulomb": [_ptr, _ptr, _dbl, _dbl, _i64, _i64, _ptr, _ptr, _i64, _ptr],
+    "qs_launch_count": [],
+    "qs_kernel_timing_enable": [_int],
+    "qs_kernel_timing_read": [_int, ctypes.POINTER(_dbl), ctypes.POINTER(_dbl), ctypes.POINTER(_i64)],
     "qs_probe_dmma_tflops": [ctypes.POINTER(_dbl), _ptr],
     "qs_probe_copy_gbs": [ctypes.POINTER(_dbl), _ptr, _i64, _ptr],
 }
@@ -61,7 +66,7 @@ def load():
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing: fail loudly
         fn.argtypes = argtypes
-        fn.restype = ctypes.c_char_p if name == "qs_last_error" else ctypes.c_int
+        fn.restype = {"qs_last_error": ctypes.c_char_p, "qs_launch_count": ctypes.c_int64}.get(name, ctypes.c_int)
     _LIB = lib
     return lib
 

@@ -34,6 +34,7 @@ void qs_set_error(const char* fmt, ...);
 
 #define QS_LAUNCH_CHECK()                                                                      \
     do {                                                                                       \
+        qs_count_launch();                                                                     \
         cudaError_t _e = cudaGetLastError();                                                   \
         if (_e != cudaSuccess) {                                                               \
             qs_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, \
@@ -45,6 +46,12 @@ void qs_set_error(const char* fmt, ...);
 static inline int64_t qs_round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 static inline int64_t qs_ceil_div(int64_t v, int64_t m) { return (v + m - 1) / m; }
 static inline int qs_elem_doubles(int dtype) { return dtype == QS_C128 ? 2 : 1; }
+
+// Instrumentation (core.cu): every kernel launch is counted; when timing is enabled the launch
+// sites of a kernel family bracket themselves with CUDA events on the launching stream.
+void qs_count_launch();
+bool qs_timing_begin(int family, double work, void* stream, int* slot);
+void qs_timing_end(int slot, void* stream);
 
 // Number of SMs of the current device (cached).
 int qs_sm_count();

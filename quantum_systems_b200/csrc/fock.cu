@@ -16,36 +16,41 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-template <bool H_COMPLEX, bool U_COMPLEX, bool SPATIAL>
-__global__ void __launch_bounds__(256) fock_kernel(const double* __restrict__ h, const double* __restrict__ u,
-                                                   double* __restrict__ f, int n, int n_occ, long long p_begin,
-                                                   long long p_end) {
+// direct term element (p, i, q) at ud[p*a0 + i*a1 + q*a2], exchange term at ue[p*b0 + i*b1 + q*b2]
+struct FockStrides {
+    long long a0, a1, a2, b0, b1, b2;
+    double scale_d, scale_e;
+};
+
+template <bool H_COMPLEX, bool U_COMPLEX, bool EXCHANGE>
+__global__ void __launch_bounds__(256) fock_kernel(const double* __restrict__ h, const double* __restrict__ ud,
+                                                   const double* __restrict__ ue, double* __restrict__ f, int n,
+                                                   int n_occ, long long p_begin, long long p_end, FockStrides st) {
     const int lane = threadIdx.x & 31;
     const long long warp_global = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const long long warps_total = ((long long)gridDim.x * blockDim.x) >> 5;
     const long long rows = p_end - p_begin;
     for (long long e = warp_global; e < rows * n; e += warps_total) {
-        const long long pl = e / n;  // local row (u points at plane p_begin)
+        const long long pl = e / n;  // local row (the u pointers address plane p_begin)
         const int q = (int)(e - pl * n);
-        const double* up = u + pl * (long long)n * n * n * (U_COMPLEX ? 2 : 1);
         double sr = 0.0, si = 0.0;
         for (int i = lane; i < n_occ; i += 32) {
-            const long long direct = ((long long)i * n + q) * n + i;  // u[p,i,q,i]
+            const long long direct = pl * st.a0 + i * st.a1 + q * st.a2;
             if (U_COMPLEX) {
-                const double2 v = reinterpret_cast<const double2*>(up)[direct];
-                sr += SPATIAL ? 2.0 * v.x : v.x;
-                si += SPATIAL ? 2.0 * v.y : v.y;
+                const double2 v = reinterpret_cast<const double2*>(ud)[direct];
+                sr += st.scale_d * v.x;
+                si += st.scale_d * v.y;
             } else {
-                sr += SPATIAL ? 2.0 * up[direct] : up[direct];
+                sr += st.scale_d * ud[direct];
             }
-            if (SPATIAL) {
-                const long long exch = ((long long)i * n + i) * n + q;  // u[p,i,i,q]
+            if (EXCHANGE) {
+                const long long exch = pl * st.b0 + i * st.b1 + q * st.b2;
                 if (U_COMPLEX) {
-                    const double2 v = reinterpret_cast<const double2*>(up)[exch];
-                    sr -= v.x;
-                    si -= v.y;
+                    const double2 v = reinterpret_cast<const double2*>(ue)[exch];
+                    sr += st.scale_e * v.x;
+                    si += st.scale_e * v.y;
                 } else {
-                    sr -= up[exch];
+                    sr += st.scale_e * ue[exch];
                 }
             }
         }
@@ -63,10 +68,9 @@ __global__ void __launch_bounds__(256) fock_kernel(const double* __restrict__ h,
     }
 }
 
-template <bool SPATIAL>
-int launch_fock(const void* h, int h_dtype, const void* u, int u_dtype, int64_t n, int64_t n_occ, void* f,
-                int64_t p_begin, int64_t p_end, void* stream) {
-    QS_REQUIRE(h && u && f && n > 0, "qs_fock: bad arguments");
+int launch_fock(const void* h, int h_dtype, const void* ud, const void* ue, int u_dtype, int64_t n, int64_t n_occ,
+                void* f, int64_t p_begin, int64_t p_end, const FockStrides& strides, void* stream) {
+    QS_REQUIRE(h && ud && f && n > 0, "qs_fock: bad arguments");
     QS_REQUIRE(0 <= n_occ && n_occ <= n, "qs_fock: n_occ out of range");
     QS_REQUIRE(0 <= p_begin && p_begin <= p_end && p_end <= n, "qs_fock: bad row range");
     QS_REQUIRE(!(h_dtype == QS_F64 && u_dtype == QS_C128),
@@ -78,14 +82,24 @@ int launch_fock(const void* h, int h_dtype, const void* u, int u_dtype, int64_t 
     if (blocks > cap) blocks = cap;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const double* hp = static_cast<const double*>(h);
-    const double* up = static_cast<const double*>(u);
+    const double* dp = static_cast<const double*>(ud);
+    const double* ep = static_cast<const double*>(ue);
     double* fp = static_cast<double*>(f);
+    const int N = (int)n, NO = (int)n_occ;
+#define QS_FOCK_LAUNCH(HC, UC)                                                                                     \
+    do {                                                                                                           \
+        if (ue)                                                                                                    \
+            fock_kernel<HC, UC, true><<<(unsigned)blocks, 256, 0, st>>>(hp, dp, ep, fp, N, NO, p_begin, p_end, strides);  \
+        else                                                                                                       \
+            fock_kernel<HC, UC, false><<<(unsigned)blocks, 256, 0, st>>>(hp, dp, ep, fp, N, NO, p_begin, p_end, strides); \
+    } while (0)
     if (h_dtype == QS_C128 && u_dtype == QS_C128)
-        fock_kernel<true, true, SPATIAL><<<(unsigned)blocks, 256, 0, st>>>(hp, up, fp, (int)n, (int)n_occ, p_begin, p_end);
+        QS_FOCK_LAUNCH(true, true);
     else if (h_dtype == QS_C128)
-        fock_kernel<true, false, SPATIAL><<<(unsigned)blocks, 256, 0, st>>>(hp, up, fp, (int)n, (int)n_occ, p_begin, p_end);
+        QS_FOCK_LAUNCH(true, false);
     else
-        fock_kernel<false, false, SPATIAL><<<(unsigned)blocks, 256, 0, st>>>(hp, up, fp, (int)n, (int)n_occ, p_begin, p_end);
+        QS_FOCK_LAUNCH(false, false);
+#undef QS_FOCK_LAUNCH
     QS_LAUNCH_CHECK();
     return QS_OK;
 }
@@ -94,10 +108,22 @@ int launch_fock(const void* h, int h_dtype, const void* u, int u_dtype, int64_t 
 
 extern "C" int qs_fock_general(const void* h, int h_dtype, const void* u, int u_dtype, int64_t n, int64_t n_occ, void* f,
                                int64_t p_begin, int64_t p_end, void* stream) {
-    return launch_fock<false>(h, h_dtype, u, u_dtype, n, n_occ, f, p_begin, p_end, stream);
+    // u[p,i,q,i]: p*n^3 + i*(n^2 + 1) + q*n
+    const FockStrides st = {n * n * n, n * n + 1, n, 0, 0, 0, 1.0, 0.0};
+    return launch_fock(h, h_dtype, u, nullptr, u_dtype, n, n_occ, f, p_begin, p_end, st, stream);
 }
 
 extern "C" int qs_fock_spatial(const void* h, int h_dtype, const void* u, int u_dtype, int64_t n, int64_t n_occ, void* f,
                                int64_t p_begin, int64_t p_end, void* stream) {
-    return launch_fock<true>(h, h_dtype, u, u_dtype, n, n_occ, f, p_begin, p_end, stream);
+    // 2 u[p,i,q,i] - u[p,i,i,q]: exchange at p*n^3 + i*(n^2 + n) + q
+    const FockStrides st = {n * n * n, n * n + 1, n, n * n * n, n * n + n, 1, 2.0, -1.0};
+    return launch_fock(h, h_dtype, u, u, u_dtype, n, n_occ, f, p_begin, p_end, st, stream);
+}
+
+extern "C" int qs_fock_gathered(const void* h, int h_dtype, const void* direct, const void* exchange, int u_dtype,
+                                int64_t n, int64_t n_occ, double scale_direct, double scale_exchange, void* f,
+                                void* stream) {
+    // direct[i,p,q] = u[p,i,q,i] and exchange[i,p,q] = u[p,i,i,q] gathered by the caller: (n_occ, n, n) blocks
+    const FockStrides st = {n, n * n, 1, n, n * n, 1, scale_direct, scale_exchange};
+    return launch_fock(h, h_dtype, direct, exchange, u_dtype, n, n_occ, f, 0, n, st, stream);
 }

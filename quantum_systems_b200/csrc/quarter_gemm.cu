@@ -16,6 +16,8 @@
 //     ring (a 5th warp would cap the kernel at 168 registers/thread and spill); 2 CTAs per SM
 //     so one CTA's epilogue overlaps the other's main loop;
 //   * the epilogue writes the new index as the slowest axis (or any 2-level strided address).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -28,12 +30,16 @@ constexpr int kThreads = kConsumerWarps * 32;
 constexpr int kATileBytes = kBlockX * kChunkK * 8;  // 16 KiB
 
 struct QuarterParams {
-    const double* image;      // [tiles_w][nchunks][2][NT][32][2] doubles
+    const double* image;      // [tiles_w][nchunks][2][NT][32][2] doubles (this launch's tile group)
     double* out;
     uint32_t X;               // rows of A
-    uint32_t Wp;              // real columns of the image actually valid (W or 2W)
+    uint32_t Wp;              // real columns actually valid (W or 2W)
+    uint32_t w_first;         // first real column of this launch's tile group
+    uint32_t tiles_x;         // ceil(X / 128)
     int nchunks;              // ceil(K'/16)
-    int tiles_w;
+    int last_halves;          // 8-k' halves of the last chunk that hold data (1 or 2)
+    int tiles_w;              // column tiles in this group, each 8*NT wide
+    long long stagger_clocks; // start delay of the second CTA wave (0 = none)
     // store address = (w/w_inner)*sw1 + (w%w_inner)*sw0 + (x/x_inner)*sx1 + (x%x_inner)*sx0
     // in OUTPUT ELEMENTS (w = w' for real output, w'/2 for complex output)
     uint32_t x_inner, w_inner;
@@ -58,9 +64,7 @@ quarter_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const QuarterPara
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int tile_w = blockIdx.x % p.tiles_w;
-    const uint32_t tile_x = blockIdx.x / p.tiles_w;
-    const uint32_t x0 = tile_x * kBlockX;
+    const uint32_t total_tiles = p.tiles_x * (uint32_t)p.tiles_w;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -68,35 +72,47 @@ quarter_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const QuarterPara
             mbar_init(bar_base + 8 * (kStages + s), kConsumerWarps);
         }
         mbar_fence_init();
+        prefetch_tensormap(&map_a);
     }
     __syncthreads();
 
-    // ===== TMA producer role (thread 0): chunk c goes to stage c % kStages =====
-    const double* img = p.image + (size_t)tile_w * p.nchunks * (kBTileBytes / 8);
-    auto produce = [&](int c) {
-        const int s = c % kStages;
+    // Persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The chunk ring runs straight
+    // across tile boundaries, so the loads of the next tile are in flight during this tile's epilogue.
+    // ===== TMA producer role (thread 0): the pj-th chunk of this CTA goes to stage pj % kStages =====
+    uint32_t pj = 0, ptile = blockIdx.x;
+    int pc = 0;
+    auto produce_next = [&]() {
+        if (ptile >= total_tiles) return;
+        const uint32_t s = pj % kStages;
         const uint32_t full = bar_base + 8 * s;
-        if (c >= kStages) mbar_wait(bar_base + 8 * (kStages + s), ((c / kStages) - 1) & 1);
+        if (pj >= kStages) mbar_wait(bar_base + 8 * (kStages + s), ((pj / kStages) - 1) & 1);
+        const uint32_t tw = ptile % (uint32_t)p.tiles_w;
+        const uint32_t px0 = (ptile / (uint32_t)p.tiles_w) * kBlockX;
         mbar_expect_tx(full, kStageBytes);
         const uint32_t dst = smem_base + s * kStageBytes;
-        tma_load_2d(dst, &map_a, c * kChunkK, (int)x0, full);
-        bulk_load_1d(dst + kATileBytes, img + (size_t)c * (kBTileBytes / 8), kBTileBytes, full);
+        tma_load_2d(dst, &map_a, pc * kChunkK, (int)px0, full);
+        bulk_load_1d(dst + kATileBytes, p.image + ((size_t)tw * p.nchunks + pc) * (kBTileBytes / 8), kBTileBytes, full);
+        ++pj;
+        if (++pc == p.nchunks) {
+            pc = 0;
+            ptile += gridDim.x;
+        }
     };
     if (threadIdx.x == 0) {
-        prefetch_tensormap(&map_a);
-        for (int c = 0; c < kStages - 1 && c < p.nchunks; ++c) produce(c);
+        for (int c = 0; c < kStages - 1; ++c) produce_next();
+    }
+
+    // Co-resident CTAs (block b and b + #SMs share an SM) would otherwise run their epilogues at
+    // the same time and leave the tensor pipe idle; start the second wave half a tile late.
+    if (p.stagger_clocks > 0 && blockIdx.x >= (gridDim.x + 1) / 2) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < p.stagger_clocks) __nanosleep(256);
     }
 
     // ===== MMA: warp w owns rows [32w, 32w+32) x all 8*NT columns of the CTA tile =====
     const int g = lane >> 2;
     const int t = lane & 3;
     const int prow = row_permutation(g);
-
-    double acc[4][NT][2];
-#pragma unroll
-    for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
 
     // A fragment address inside a stage: row r = 32*warp + 8*mt + prow (128 B per row), logical
     // 16-byte chunk (4h + t) stored at chunk ^ (r & 7) by the TMA 128-byte swizzle; r & 7 == prow.
@@ -105,73 +121,90 @@ quarter_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const QuarterPara
     const uint32_t a_chunk1 = (uint32_t)(((4 + t) ^ prow) << 4);  // h = 1
     const uint32_t b_lane_off = kATileBytes + (uint32_t)lane * 16u;
 
-    for (int c = 0; c < p.nchunks; ++c) {
-        const int s = c % kStages;
-        if (threadIdx.x == 0 && c + kStages - 1 < p.nchunks) produce(c + kStages - 1);
-        __syncwarp();
-        mbar_wait(bar_base + 8 * s, (c / kStages) & 1);
-        const uint32_t stage = smem_base + s * kStageBytes;
+    uint32_t j = 0;  // chunks consumed so far by this CTA
+    for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        double acc[4][NT][2];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            double2 a[4];
-            double2 b[NT];
+        for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-            for (int mt = 0; mt < 4; ++mt)
-                a[mt] = lds_128(stage + a_row_off + mt * 1024u + (h ? a_chunk1 : a_chunk0));
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt)
-                b[nt] = lds_128(stage + b_lane_off + (uint32_t)(h * NT + nt) * 512u);
-#pragma unroll
-            for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) dmma_8x8x4(acc[mt][nt][0], acc[mt][nt][1], a[mt].x, b[nt].x);
-#pragma unroll
-            for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) dmma_8x8x4(acc[mt][nt][0], acc[mt][nt][1], a[mt].y, b[nt].y);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_base + 8 * (kStages + s));
-    }
+            for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
 
-    // ===== epilogue: rotated / strided store straight from the accumulators =====
-    long long xoff[4];
-    bool xok[4];
+        for (int c = 0; c < p.nchunks; ++c, ++j) {
+            const uint32_t s = j % kStages;
+            if (threadIdx.x == 0) produce_next();
+            __syncwarp();
+            mbar_wait(bar_base + 8 * s, (j / kStages) & 1);
+            const uint32_t stage = smem_base + s * kStageBytes;
+            // the last chunk may hold <= 8 valid k': skip its all-zero second half
+            const int halves = (c == p.nchunks - 1) ? p.last_halves : 2;
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt) {
-        const uint32_t x = x0 + 32 * warp + 8 * mt + prow;
-        xok[mt] = x < p.X;
-        const uint32_t xq = x / p.x_inner;
-        const uint32_t xr = x - xq * p.x_inner;
-        xoff[mt] = (long long)xq * p.sx1 + (long long)xr * p.sx0;
-    }
-    const uint32_t wbase = (uint32_t)tile_w * (8 * NT);
+            for (int h = 0; h < 2; ++h) {
+                if (h < halves) {
+                    double2 a[4];
+                    double2 b[NT];
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-        const uint32_t wp = wbase + 8 * nt + 2 * t;  // real column of acc[..][nt][0]; wp + 1 for [1]
-        if (COMPLEX_OUT) {
-            if (wp < p.Wp) {
-                const uint32_t w = wp >> 1;
-                const uint32_t wq = w / p.w_inner;
-                const uint32_t wr = w - wq * p.w_inner;
-                const long long woff = (long long)wq * p.sw1 + (long long)wr * p.sw0;
+                    for (int mt = 0; mt < 4; ++mt)
+                        a[mt] = lds_128(stage + a_row_off + mt * 1024u + (h ? a_chunk1 : a_chunk0));
 #pragma unroll
-                for (int mt = 0; mt < 4; ++mt)
-                    if (xok[mt])
-                        *reinterpret_cast<double2*>(p.out + 2 * (woff + xoff[mt])) =
-                            make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+                    for (int nt = 0; nt < NT; ++nt)
+                        b[nt] = lds_128(stage + b_lane_off + (uint32_t)(h * NT + nt) * 512u);
+#pragma unroll
+                    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt)
+                            dmma_8x8x4(acc[mt][nt][0], acc[mt][nt][1], a[mt].x, b[nt].x);
+#pragma unroll
+                    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt)
+                            dmma_8x8x4(acc[mt][nt][0], acc[mt][nt][1], a[mt].y, b[nt].y);
+                }
             }
-        } else {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_base + 8 * (kStages + s));
+        }
+
+        // ===== epilogue: rotated / strided store straight from the accumulators =====
+        const uint32_t tile_w = tile % (uint32_t)p.tiles_w;
+        const uint32_t x0 = (tile / (uint32_t)p.tiles_w) * kBlockX;
+        long long xoff[4];
+        bool xok[4];
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const uint32_t w = wp + e;
-                if (w < p.Wp) {
+        for (int mt = 0; mt < 4; ++mt) {
+            const uint32_t x = x0 + 32 * warp + 8 * mt + prow;
+            xok[mt] = x < p.X;
+            const uint32_t xq = x / p.x_inner;
+            const uint32_t xr = x - xq * p.x_inner;
+            xoff[mt] = (long long)xq * p.sx1 + (long long)xr * p.sx0;
+        }
+        const uint32_t wbase = p.w_first + tile_w * (8 * NT);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const uint32_t wp = wbase + 8 * nt + 2 * t;  // real column of acc[..][nt][0]; wp + 1 for [1]
+            if (COMPLEX_OUT) {
+                if (wp < p.Wp) {
+                    const uint32_t w = wp >> 1;
                     const uint32_t wq = w / p.w_inner;
                     const uint32_t wr = w - wq * p.w_inner;
                     const long long woff = (long long)wq * p.sw1 + (long long)wr * p.sw0;
 #pragma unroll
                     for (int mt = 0; mt < 4; ++mt)
-                        if (xok[mt]) p.out[woff + xoff[mt]] = acc[mt][nt][e];
+                        if (xok[mt])
+                            *reinterpret_cast<double2*>(p.out + 2 * (woff + xoff[mt])) =
+                                make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const uint32_t w = wp + e;
+                    if (w < p.Wp) {
+                        const uint32_t wq = w / p.w_inner;
+                        const uint32_t wr = w - wq * p.w_inner;
+                        const long long woff = (long long)wq * p.sw1 + (long long)wr * p.sw0;
+#pragma unroll
+                        for (int mt = 0; mt < 4; ++mt)
+                            if (xok[mt]) p.out[woff + xoff[mt]] = acc[mt][nt][e];
+                    }
                 }
             }
         }
@@ -179,16 +212,15 @@ quarter_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const QuarterPara
 }
 
 // ---------------------------------------------------------------------------------------------
-// coefficient image: real (K', W') expansion of M laid out in MMA fragment order
-//   image[tile_w][chunk][h][nt][lane][e] = M'[16*chunk + 8h + 2t + e][8*NT*tile_w + 8nt + g]
+// coefficient image: real (K', W') expansion of M laid out in MMA fragment order, per tile group
+//   image[tile][chunk][h][nt][lane][e] = M'[16*chunk + 8h + 2t + e][w_first + 8*NT*tile + 8nt + g]
 // ---------------------------------------------------------------------------------------------
 struct ImageParams {
     const double* m;
     long long sk, sw;  // element strides of M[k, w]
     int m_complex, a_complex, conj;
-    int K, W;          // logical (complex or real) extents
     int Kp, Wp;        // real extents: K * (a_complex ? 2 : 1), W * (out_complex ? 2 : 1)
-    int NT, nchunks, tiles_w;
+    int NT, nchunks, tiles_w, w_first;
     int coulomb;       // 1: M[k, w] = alpha / sqrt((m[k] - m[w])^2 + a^2), m = grid (ODQD interaction)
     double alpha, a2;
 };
@@ -233,7 +265,7 @@ __global__ void build_image_kernel(ImageParams q, double* __restrict__ image) {
         const int tw = r / q.nchunks;
         const int g = lane >> 2, t = lane & 3;
         const int kp = 16 * chunk + 8 * h + 2 * t + e;
-        const int wp = 8 * q.NT * tw + 8 * nt + g;
+        const int wp = q.w_first + 8 * q.NT * tw + 8 * nt + g;
         image[i] = image_value(q, kp, wp);
     }
 }
@@ -241,8 +273,18 @@ __global__ void build_image_kernel(ImageParams q, double* __restrict__ image) {
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+// The W' real columns are cut into 8-wide MMA column tiles; those are dealt to CTA tiles of NT <= 8
+// column tiles each, in at most two groups whose NT differ by one (e.g. W' = 400 -> 6 x NT=7 + 1 x NT=8),
+// so no CTA tile carries more than 7 padding columns.  Each group is one persistent launch.
+struct TileGroup {
+    int NT, tiles_w, w_first;
+    int64_t image_offset;  // doubles
+};
+
 struct Tiling {
-    int Kp, Wp, NT, tiles_w, nchunks;
+    int Kp, Wp, nchunks, last_halves, ngroups;
+    TileGroup group[2];
+    int64_t image_doubles;
 };
 
 Tiling make_tiling(int64_t K, int64_t W, int a_dtype, int m_dtype) {
@@ -250,9 +292,22 @@ Tiling make_tiling(int64_t K, int64_t W, int a_dtype, int m_dtype) {
     const bool out_complex = a_dtype == QS_C128 || m_dtype == QS_C128;
     tl.Kp = (int)(K * (a_dtype == QS_C128 ? 2 : 1));
     tl.Wp = (int)(W * (out_complex ? 2 : 1));
-    tl.tiles_w = (int)qs_ceil_div(tl.Wp, 64);
-    tl.NT = (int)qs_ceil_div(qs_ceil_div(tl.Wp, tl.tiles_w), 8);
     tl.nchunks = (int)qs_ceil_div(tl.Kp, kChunkK);
+    tl.last_halves = (tl.Kp - (tl.nchunks - 1) * kChunkK) <= 8 ? 1 : 2;
+    const int col_tiles = (int)qs_ceil_div(tl.Wp, 8);
+    const int cta_tiles = (int)qs_ceil_div(col_tiles, 8);
+    const int base = col_tiles / cta_tiles, extra = col_tiles % cta_tiles;
+    tl.ngroups = 0;
+    int64_t off = 0;
+    int w = 0;
+    if (extra > 0) {
+        tl.group[tl.ngroups++] = {base + 1, extra, w, off};
+        off += (int64_t)extra * tl.nchunks * 128 * (base + 1);
+        w += extra * (base + 1) * 8;
+    }
+    tl.group[tl.ngroups++] = {base, cta_tiles - extra, w, off};
+    off += (int64_t)(cta_tiles - extra) * tl.nchunks * 128 * base;
+    tl.image_doubles = off;
     return tl;
 }
 
@@ -273,35 +328,64 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
+int g_stagger = 1;  // QS_STAGGER=0 disables the second-wave start delay (tuning aid)
+
 template <int NT, bool CO>
-int launch_variant(const CUtensorMap& map, const QuarterParams& p, int64_t grid, cudaStream_t st) {
+int launch_variant(const CUtensorMap& map, QuarterParams p, cudaStream_t st) {
     constexpr int smem = kStages * (kATileBytes + NT * 1024) + 2 * kStages * 8 + 1024;
     static bool configured = false;
     if (!configured) {
         QS_CUDA(cudaFuncSetAttribute(quarter_gemm_kernel<NT, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         QS_CUDA(cudaFuncSetAttribute(quarter_gemm_kernel<NT, CO>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      cudaSharedmemCarveoutMaxShared));
+        const char* env = getenv("QS_STAGGER");
+        if (env) g_stagger = atoi(env);
         configured = true;
     }
+    const int64_t total = (int64_t)p.tiles_x * p.tiles_w;
+    const int64_t resident = 2LL * qs_sm_count();
+    const int64_t grid = total < resident ? total : resident;
+    // half a tile of tensor-pipe time when two CTAs share an SM: nchunks * (4 * NT * 4 DMMA) * 16 clk
+    p.stagger_clocks = (g_stagger && grid > resident / 2) ? (long long)p.nchunks * NT * 256 : 0;
     quarter_gemm_kernel<NT, CO><<<(unsigned)grid, kThreads, smem, st>>>(map, p);
     QS_LAUNCH_CHECK();
     return QS_OK;
 }
 
 template <bool CO>
-int launch_nt(int NT, const CUtensorMap& map, const QuarterParams& p, int64_t grid, cudaStream_t st) {
+int launch_nt(int NT, const CUtensorMap& map, const QuarterParams& p, cudaStream_t st) {
     switch (NT) {
-        case 1: return launch_variant<1, CO>(map, p, grid, st);
-        case 2: return launch_variant<2, CO>(map, p, grid, st);
-        case 3: return launch_variant<3, CO>(map, p, grid, st);
-        case 4: return launch_variant<4, CO>(map, p, grid, st);
-        case 5: return launch_variant<5, CO>(map, p, grid, st);
-        case 6: return launch_variant<6, CO>(map, p, grid, st);
-        case 7: return launch_variant<7, CO>(map, p, grid, st);
-        case 8: return launch_variant<8, CO>(map, p, grid, st);
+        case 1: return launch_variant<1, CO>(map, p, st);
+        case 2: return launch_variant<2, CO>(map, p, st);
+        case 3: return launch_variant<3, CO>(map, p, st);
+        case 4: return launch_variant<4, CO>(map, p, st);
+        case 5: return launch_variant<5, CO>(map, p, st);
+        case 6: return launch_variant<6, CO>(map, p, st);
+        case 7: return launch_variant<7, CO>(map, p, st);
+        case 8: return launch_variant<8, CO>(map, p, st);
     }
     qs_set_error("internal: NT=%d out of range", NT);
     return QS_ERR_INVALID;
+}
+
+int build_image(ImageParams q, const Tiling& tl, void* image, void* stream) {
+    q.Kp = tl.Kp;
+    q.Wp = tl.Wp;
+    q.nchunks = tl.nchunks;
+    for (int gi = 0; gi < tl.ngroups; ++gi) {
+        const TileGroup& gr = tl.group[gi];
+        q.NT = gr.NT;
+        q.tiles_w = gr.tiles_w;
+        q.w_first = gr.w_first;
+        const long long total = (long long)gr.tiles_w * tl.nchunks * 128 * gr.NT;
+        long long blocks = qs_ceil_div(total, 256);
+        const long long cap = (long long)qs_sm_count() * 16;
+        if (blocks > cap) blocks = cap;
+        build_image_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            q, static_cast<double*>(image) + gr.image_offset);
+        QS_LAUNCH_CHECK();
+    }
+    return QS_OK;
 }
 
 }  // namespace
@@ -310,7 +394,7 @@ extern "C" int qs_coeff_image_bytes(int64_t K, int64_t W, int a_dtype, int m_dty
     QS_REQUIRE(K > 0 && W > 0 && bytes, "qs_coeff_image_bytes: bad arguments");
     QS_REQUIRE(K < (1 << 24) && W < (1 << 24), "qs_coeff_image_bytes: K or W too large");
     const Tiling tl = make_tiling(K, W, a_dtype, m_dtype);
-    *bytes = (int64_t)tl.tiles_w * tl.nchunks * 128 * tl.NT * 8;
+    *bytes = tl.image_doubles * 8;
     return QS_OK;
 }
 
@@ -319,29 +403,28 @@ extern "C" int qs_build_coeff_image(const void* m, int m_dtype, int64_t m_sk, in
     QS_REQUIRE(m && image && K > 0 && W > 0, "qs_build_coeff_image: bad arguments");
     const Tiling tl = make_tiling(K, W, a_dtype, m_dtype);
     ImageParams q;
+    memset(&q, 0, sizeof(q));
     q.m = static_cast<const double*>(m);
     q.sk = m_sk;
     q.sw = m_sw;
     q.m_complex = m_dtype == QS_C128;
     q.a_complex = a_dtype == QS_C128;
     q.conj = m_conj;
-    q.K = (int)K;
-    q.W = (int)W;
-    q.Kp = tl.Kp;
-    q.Wp = tl.Wp;
-    q.NT = tl.NT;
-    q.nchunks = tl.nchunks;
-    q.tiles_w = tl.tiles_w;
-    q.coulomb = 0;
-    q.alpha = q.a2 = 0.0;
-    const long long total = (long long)tl.tiles_w * tl.nchunks * 128 * tl.NT;
-    const int threads = 256;
-    long long blocks = qs_ceil_div(total, threads);
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    build_image_kernel<<<(unsigned)blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
-        q, static_cast<double*>(image));
-    QS_LAUNCH_CHECK();
-    return QS_OK;
+    return build_image(q, tl, image, stream);
+}
+
+// Coefficient image of the shielded-Coulomb matrix W[p, q] on `grid` (real, Gp x Gp), never
+// materialised as a dense matrix.  Internal entry used by qs_odqd_coulomb.
+int qs_build_coulomb_image(const double* grid, double alpha, double a, int64_t Gp, void* image, void* stream) {
+    QS_REQUIRE(grid && image && Gp > 0, "qs_build_coulomb_image: bad arguments");
+    const Tiling tl = make_tiling(Gp, Gp, QS_F64, QS_F64);
+    ImageParams q;
+    memset(&q, 0, sizeof(q));
+    q.m = grid;
+    q.coulomb = 1;
+    q.alpha = alpha;
+    q.a2 = a * a;
+    return build_image(q, tl, image, stream);
 }
 
 extern "C" int qs_quarter_transform(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda, const void* image,
@@ -377,44 +460,32 @@ extern "C" int qs_quarter_transform(const void* A, int a_dtype, int64_t X, int64
         return QS_ERR_CUDA;
     }
 
-    QuarterParams p;
-    p.image = static_cast<const double*>(image);
-    p.out = static_cast<double*>(out);
-    p.X = (uint32_t)X;
-    p.Wp = (uint32_t)tl.Wp;
-    p.nchunks = tl.nchunks;
-    p.tiles_w = tl.tiles_w;
-    p.x_inner = (uint32_t)x_inner;
-    p.w_inner = (uint32_t)w_inner;
-    p.sx0 = sx0;
-    p.sx1 = sx1;
-    p.sw0 = sw0;
-    p.sw1 = sw1;
-    const int64_t grid = qs_ceil_div(X, kBlockX) * tl.tiles_w;
-    QS_REQUIRE(grid < (1LL << 31), "qs_quarter_transform: grid too large");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    return out_complex ? launch_nt<true>(tl.NT, map, p, grid, st) : launch_nt<false>(tl.NT, map, p, grid, st);
-}
-
-// Coefficient image of the shielded-Coulomb matrix W[p, q] on `grid` (real, Gp x Gp), never
-// materialised as a dense matrix.  Internal entry used by qs_odqd_coulomb.
-int qs_build_coulomb_image(const double* grid, double alpha, double a, int64_t Gp, void* image, void* stream) {
-    QS_REQUIRE(grid && image && Gp > 0, "qs_build_coulomb_image: bad arguments");
-    const Tiling tl = make_tiling(Gp, Gp, QS_F64, QS_F64);
-    ImageParams q;
-    memset(&q, 0, sizeof(q));
-    q.m = grid;
-    q.K = q.W = q.Kp = q.Wp = (int)Gp;
-    q.NT = tl.NT;
-    q.nchunks = tl.nchunks;
-    q.tiles_w = tl.tiles_w;
-    q.coulomb = 1;
-    q.alpha = alpha;
-    q.a2 = a * a;
-    const long long total = (long long)tl.tiles_w * tl.nchunks * 128 * tl.NT;
-    long long blocks = qs_ceil_div(total, 256);
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    build_image_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(q, static_cast<double*>(image));
-    QS_LAUNCH_CHECK();
+    int span = -1;
+    qs_timing_begin(QS_FAMILY_QUARTER_GEMM, 2.0 * (double)X * tl.Kp * tl.Wp, stream, &span);
+    for (int gi = 0; gi < tl.ngroups; ++gi) {
+        const TileGroup& gr = tl.group[gi];
+        QuarterParams p;
+        p.image = static_cast<const double*>(image) + gr.image_offset;
+        p.out = static_cast<double*>(out);
+        p.X = (uint32_t)X;
+        p.Wp = (uint32_t)tl.Wp;
+        p.w_first = (uint32_t)gr.w_first;
+        p.tiles_x = (uint32_t)qs_ceil_div(X, kBlockX);
+        p.nchunks = tl.nchunks;
+        p.last_halves = tl.last_halves;
+        p.tiles_w = gr.tiles_w;
+        p.stagger_clocks = 0;
+        p.x_inner = (uint32_t)x_inner;
+        p.w_inner = (uint32_t)w_inner;
+        p.sx0 = sx0;
+        p.sx1 = sx1;
+        p.sw0 = sw0;
+        p.sw1 = sw1;
+        QS_REQUIRE((int64_t)p.tiles_x * p.tiles_w < (1LL << 31), "qs_quarter_transform: too many tiles");
+        const int rc = out_complex ? launch_nt<true>(gr.NT, map, p, st) : launch_nt<false>(gr.NT, map, p, st);
+        if (rc) return rc;
+    }
+    qs_timing_end(span, stream);
     return QS_OK;
 }

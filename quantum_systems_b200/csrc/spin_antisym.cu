@@ -164,6 +164,41 @@ __global__ void add_spin_one_body_kernel(const double* __restrict__ h, double* _
     }
 }
 
+// spin_2_tb[p,q,r,s] = sum_i S_i[p,r] S_i[q,s]  (- sum_i S_i[p,s] S_i[q,r] when anti-symmetrised), i in {x,y,z}
+// (reference basis_set.py:743-747 and :523-526).  One block per (p, q): the six needed rows live in
+// shared memory, the (r, s) plane is written with coalesced 16-byte stores.  Write-bound: 16 n^4 bytes.
+__global__ void __launch_bounds__(256) spin2_tb_kernel(const double2* __restrict__ sx, const double2* __restrict__ sy,
+                                                       const double2* __restrict__ sz, double2* __restrict__ out, int n,
+                                                       int antisym, long long p_begin) {
+    extern __shared__ double2 rows[];  // [6][n]: S_i[p,:] for i = x,y,z then S_i[q,:]
+    const long long pq = blockIdx.x;
+    const int p = (int)(p_begin + pq / n), q = (int)(pq % n);
+    const double2* mats[3] = {sx, sy, sz};
+    for (int j = threadIdx.x; j < 3 * n; j += blockDim.x) {
+        const int i = j / n, c = j - i * n;
+        rows[i * n + c] = mats[i][(long long)p * n + c];
+        rows[(3 + i) * n + c] = mats[i][(long long)q * n + c];
+    }
+    __syncthreads();
+    double2* plane = out + pq * (long long)n * n;
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+        const int r = e / n, s = e - r * n;
+        double re = 0.0, im = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const double2 a = rows[i * n + r], b = rows[(3 + i) * n + s];
+            re += a.x * b.x - a.y * b.y;
+            im += a.x * b.y + a.y * b.x;
+            if (antisym) {
+                const double2 c = rows[i * n + s], d = rows[(3 + i) * n + r];
+                re -= c.x * d.x - c.y * d.y;
+                im -= c.x * d.y + c.y * d.x;
+            }
+        }
+        plane[e] = make_double2(re, im);
+    }
+}
+
 }  // namespace
 
 extern "C" int qs_add_spin_two_body(const void* u, int in_dtype, int64_t l, void* out, int out_dtype, int anti_symmetrize,
@@ -179,6 +214,14 @@ extern "C" int qs_add_spin_two_body(const void* u, int in_dtype, int64_t l, void
     const double* in = static_cast<const double*>(u);
     double* o = static_cast<double*>(out);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int span = -1;
+    {
+        // algorithmic bytes: the spatial planes read once + every output element written once
+        const double n4 = (double)planes * 8.0 * l * l * l;  // output elements
+        qs_timing_begin(QS_FAMILY_SPIN_PASS,
+                        n4 / 16.0 * 8.0 * qs_elem_doubles(in_dtype) + n4 * 8.0 * qs_elem_doubles(out_dtype), stream,
+                        &span);
+    }
     // gridDim.z is limited to 65535 and gridDim.y too: l <= 32767 covers y; chunk z
     for (int64_t z0 = 0; z0 < planes; z0 += 65535) {
         const int64_t nz = planes - z0 < 65535 ? planes - z0 : 65535;
@@ -202,6 +245,7 @@ extern "C" int qs_add_spin_two_body(const void* u, int in_dtype, int64_t l, void
 #undef QS_SPIN_LAUNCH
         QS_LAUNCH_CHECK();
     }
+    qs_timing_end(span, stream);
     return QS_OK;
 }
 
@@ -215,6 +259,9 @@ extern "C" int qs_anti_symmetrize(const void* u, int dtype, int64_t n, void* out
     const dim3 block(32, 8);
     const dim3 grid((unsigned)(tiles * tiles), (unsigned)n, (unsigned)(p_end - p_begin));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int span = -1;
+    qs_timing_begin(QS_FAMILY_SPIN_PASS, 2.0 * (double)(p_end - p_begin) * n * n * n * 8.0 * qs_elem_doubles(dtype),
+                    stream, &span);
     if (dtype == QS_C128)
         antisym_kernel<true><<<grid, block, 0, st>>>(static_cast<const double*>(u), static_cast<double*>(out), (int)n,
                                                      tiles, p_begin);
@@ -222,6 +269,7 @@ extern "C" int qs_anti_symmetrize(const void* u, int dtype, int64_t n, void* out
         antisym_kernel<false><<<grid, block, 0, st>>>(static_cast<const double*>(u), static_cast<double*>(out), (int)n,
                                                       tiles, p_begin);
     QS_LAUNCH_CHECK();
+    qs_timing_end(span, stream);
     return QS_OK;
 }
 
@@ -240,6 +288,24 @@ extern "C" int qs_add_spin_one_body(const void* h, int in_dtype, int64_t l, void
         add_spin_one_body_kernel<false, true><<<(unsigned)blocks, 256, 0, st>>>(in, o, (int)l);
     else
         add_spin_one_body_kernel<false, false><<<(unsigned)blocks, 256, 0, st>>>(in, o, (int)l);
+    QS_LAUNCH_CHECK();
+    return QS_OK;
+}
+
+extern "C" int qs_spin_squared_two_body(const void* sx, const void* sy, const void* sz, int64_t n, int anti_symmetrize,
+                                        void* out, int64_t p_begin, int64_t p_end, void* stream) {
+    QS_REQUIRE(sx && sy && sz && out && n > 0, "qs_spin_squared_two_body: bad arguments");
+    QS_REQUIRE(0 <= p_begin && p_begin <= p_end && p_end <= n, "qs_spin_squared_two_body: bad plane range");
+    if (p_begin == p_end) return QS_OK;
+    const int smem = 6 * (int)n * 16;
+    QS_REQUIRE(smem <= 200 * 1024, "qs_spin_squared_two_body: n too large");
+    if (smem > 48 * 1024)
+        QS_CUDA(cudaFuncSetAttribute(spin2_tb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const long long blocks = (p_end - p_begin) * n;
+    QS_REQUIRE(blocks < (1LL << 31), "qs_spin_squared_two_body: grid too large");
+    spin2_tb_kernel<<<(unsigned)blocks, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const double2*>(sx), static_cast<const double2*>(sy), static_cast<const double2*>(sz),
+        static_cast<double2*>(out), (int)n, anti_symmetrize, p_begin);
     QS_LAUNCH_CHECK();
     return QS_OK;
 }

@@ -1,0 +1,82 @@
+"""``ODQD`` -- one-dimensional quantum dot on a grid (mirror of reference
+quantum_dots/one_dim/one_dim_qd.py:169-289).
+
+Host side (numpy/scipy, O(G l)): grid, potential, tridiagonal eigenproblem -- exactly the reference's
+recipe.  Device side: the O(l^2 G^2 + l^4 G) shielded-Coulomb build ``u_abcd`` runs as two chained
+FP64 tensor-core GEMMs (``ops.odqd_coulomb``) instead of ``np.einsum``.
+"""
+
+import numpy as _numpy
+import scipy.linalg
+
+from . import _arrays, ops, potentials
+from .basis_set import BasisSet
+
+
+class ODQD(BasisSet):
+    """Create a 1-D quantum-dot basis of the ``l`` lowest eigenfunctions of ``potential`` on
+    ``linspace(-grid_length, grid_length, num_grid_points)``.
+
+    Parameters (one_dim_qd.py:172-186)
+    ----------
+    l : int
+        Number of basis functions.
+    grid_length : int or float
+        Half-width of the grid.
+    num_grid_points : int
+        Number of grid points (the two end points carry zero amplitude).
+    a : float, default 0.25
+        Screening parameter of the shielded Coulomb interaction.
+    alpha : float, default 1.0
+        Strength of the shielded Coulomb interaction.
+    beta : float, default 0.0
+        Strength of the non-dipole ``x^2`` term in the position operator.
+    potential : callable
+        Confinement; defaults to ``HOPotential(omega=0.25)``.
+    """
+
+    HOPotential = potentials.HOPotential
+    DWPotential = potentials.DWPotential
+    DWPotentialSmooth = potentials.DWPotentialSmooth
+    SymmetricDWPotential = potentials.SymmetricDWPotential
+    AsymmetricDWPotential = potentials.AsymmetricDWPotential
+    GaussianPotential = potentials.GaussianPotential
+    AtomicPotential = potentials.AtomicPotential
+
+    def __init__(self, l, grid_length, num_grid_points, a=0.25, alpha=1.0, beta=0, potential=None, **kwargs):
+        super().__init__(l, dim=1, **kwargs)
+        self.a = a
+        self.alpha = alpha
+        self.grid_length = grid_length
+        self.num_grid_points = num_grid_points
+        self.grid = _numpy.linspace(-self.grid_length, self.grid_length, self.num_grid_points)
+        self.beta = beta
+        if potential is None:
+            potential = potentials.HOPotential(0.25)  # Zanghellini et al. frequency, one_dim_qd.py:248-252
+        self.potential = potential
+        self.setup_basis()
+
+    def setup_basis(self):
+        """Fill ``h, s, u, spf, position`` (one_dim_qd.py:258-289)."""
+        inner = self.grid[1:-1]
+        dx = self.grid[1] - self.grid[0]
+
+        # finite-difference Hamiltonian on the interior points; l lowest eigenpairs (host, O(G l))
+        diagonal = 1.0 / (dx**2) + self.potential(inner)
+        off_diagonal = -1.0 / (2 * dx**2) * _numpy.ones(self.num_grid_points - 3)
+        eps, C = scipy.linalg.eigh_tridiagonal(diagonal, off_diagonal, select="i", select_range=(0, self.l - 1))
+        self.eigen_energies = eps
+
+        spf = _numpy.zeros((self.l, self.num_grid_points), dtype=_numpy.complex128)
+        spf[:, 1:-1] = C.T / _numpy.sqrt(dx)
+        self.spf = spf
+        self.h = _numpy.diag(eps).astype(_numpy.complex128)
+        self.s = _numpy.eye(self.l)
+
+        # shielded-Coulomb two-body elements: two chained DMMA GEMMs on the device
+        u = ops.odqd_coulomb(_arrays.to_device(C), _arrays.to_device(inner), self.alpha, self.a)
+        self.u = _arrays.to_module(u, self.np)
+
+        position = _numpy.zeros((1, self.l, self.l), dtype=_numpy.complex128)
+        position[0] = (C.T * (inner + self.beta * inner**2)) @ C  # <a| x + beta x^2 |b>, O(G l^2) host
+        self.position = position

@@ -233,3 +233,67 @@ def probe_copy_gbs(nbytes=1 << 32):
     val = ctypes.c_double(0.0)
     _native.call("qs_probe_copy_gbs", ctypes.byref(val), _ptr(scratch), nbytes, _stream())
     return val.value
+
+
+def spin_squared_two_body(sx, sy, sz, anti_symmetrize=False, planes=None):
+    """``sum_i S_i[p,r] S_i[q,s]`` (minus the r<->s exchange when anti-symmetrised) from the three
+    (n, n) spin matrices (reference basis_set.py:743-747, :523-526)."""
+    mats = [_device_tensor(m, "spin matrix").to(torch.complex128).contiguous() for m in (sx, sy, sz)]
+    n = mats[0].shape[0]
+    p0, p1 = (0, n) if planes is None else planes
+    out = torch.empty((p1 - p0, n, n, n), dtype=torch.complex128, device=mats[0].device)
+    _native.call(
+        "qs_spin_squared_two_body", _ptr(mats[0]), _ptr(mats[1]), _ptr(mats[2]), n, int(bool(anti_symmetrize)),
+        _ptr(out), p0, p1, _stream(),
+    )
+    return out
+
+
+def transform_functions(spf, coeff, bra):
+    """Grid orbitals under a basis change, one quarter GEMM over the grid points.
+
+    ket (``bra=False``): ``out[p, g] = sum_a C[a, p] spf[a, g]``        (reference basis_set.py:321-323)
+    bra (``bra=True``):  ``out[p, g] = sum_a C_tilde[p, a] bra_spf[a, g]``  (reference basis_set.py:325-327)
+    """
+    spf = _device_tensor(spf, "spf")
+    coeff = _device_tensor(coeff, "coefficients")
+    n = spf.shape[0]
+    grid_shape = tuple(spf.shape[1:])
+    G = 1
+    for extent in grid_shape:
+        G *= extent
+    if bra:
+        m = coeff.shape[0]
+        if coeff.shape[1] != n:
+            raise ValueError("C_tilde must be (l_new, l_old)")
+        sk, sw = 1, n
+    else:
+        m = coeff.shape[1]
+        if coeff.shape[0] != n:
+            raise ValueError("C must be (l_old, l_new)")
+        sk, sw = m, 1
+    out_dtype = _result_dtype(spf, coeff)
+    # A[g, a] = spf[a, g]: the contracted index must be contiguous (pure data movement), pitch even for TMA
+    pitch = n if spf.dtype == torch.complex128 else n + (n & 1)
+    A = torch.zeros((G, pitch), dtype=spf.dtype, device=spf.device)
+    A[:, :n] = spf.reshape(n, G).transpose(0, 1)
+    image = coeff_image(coeff, n, m, spf.dtype, sk, sw)
+    out = torch.empty((m,) + grid_shape, dtype=out_dtype, device=spf.device)
+    quarter_transform(A, G, n, pitch, image, coeff.dtype, m, out, G, 1, 0, 1, 0, G)
+    return out
+
+
+def fock_gathered(h, direct, exchange, n_occ, scale_direct, scale_exchange, f=None):
+    """Fock reduction on pre-gathered ``(n_occ, n, n)`` blocks (host-resident ``u``: only the needed
+    elements are staged into HBM)."""
+    h = _device_tensor(h, "h")
+    direct = _device_tensor(direct, "direct")
+    exchange = _device_tensor(exchange, "exchange") if exchange is not None else None
+    n = h.shape[0]
+    if f is None:
+        f = torch.empty_like(h)
+    _native.call(
+        "qs_fock_gathered", _ptr(h), _code(h), _ptr(direct), _ptr(exchange), _code(direct), n, int(n_occ),
+        float(scale_direct), float(scale_exchange), _ptr(f), _stream(),
+    )
+    return f

@@ -1,0 +1,168 @@
+"""``QuantumSystem`` -- a ``BasisSet`` plus a particle number (mirror of reference system.py:6-250).
+
+The class is deliberately thin: it forwards the matrix elements of its basis set and keeps the
+occupied/virtual bookkeeping; the heavy methods (``change_basis``, ``construct_fock_matrix``) end in
+the CUDA kernels behind ``BasisSet`` / ``ops``.
+"""
+
+import abc
+import copy
+import types
+import typing
+
+
+class QuantumSystem(metaclass=abc.ABCMeta):
+    """Abstract base: ``n`` occupied basis functions out of ``basis_set.l`` (system.py:6-30)."""
+
+    def __init__(self, n, basis_set):
+        self._basis_set = basis_set
+        assert n <= self._basis_set.l
+        self.np = self._basis_set.np
+        self.set_system_size(n, self._basis_set.l)
+        self._time_evolution_operator = []
+        self._add_h_0 = True
+        self._add_u_0 = True
+
+    def set_system_size(self, n, l):
+        """Set ``n, l, m = l - n`` and the occupied/virtual slices ``o, v`` (system.py:32-51)."""
+        assert n <= l
+        self.n = n
+        self.l = l
+        self.m = self.l - self.n
+        self.o = slice(0, self.n)
+        self.v = slice(self.n, self.l)
+
+    @abc.abstractmethod
+    def construct_fock_matrix(self, h, u, f=None):
+        pass
+
+    def change_module(self, np):
+        """Move the system (and its basis set) to another array module (system.py:57-67)."""
+        self.np = np
+        self._basis_set.change_module(self.np)
+
+    def change_basis(self, C, C_tilde=None):
+        """Basis change of every matrix element; ``o``/``v`` follow the new ``l`` (system.py:69-71)."""
+        self._basis_set.change_basis(C, C_tilde)
+        self.set_system_size(self.n, self._basis_set.l)
+
+    @abc.abstractmethod
+    def change_to_hf_basis(self, *args, **kwargs):
+        pass
+
+    @abc.abstractmethod
+    def compute_reference_energy(self, h=None, u=None):
+        pass
+
+    def compute_particle_density(self, rho_qp, C=None, C_tilde=None):
+        return self._basis_set.compute_particle_density(rho_qp, C=C, C_tilde=C_tilde)
+
+    # forwarding properties (system.py:86-142)
+    @property
+    def dim(self):
+        return self._basis_set.dim
+
+    @property
+    def grid(self):
+        return self._basis_set.grid
+
+    @property
+    def h(self):
+        """One-body Hamiltonian."""
+        return self._basis_set.h
+
+    @property
+    def u(self):
+        """Two-body Hamiltonian."""
+        return self._basis_set.u
+
+    @property
+    def s(self):
+        """Overlap matrix."""
+        return self._basis_set.s
+
+    @property
+    def position(self):
+        return self._basis_set.position
+
+    @property
+    def momentum(self):
+        return self._basis_set.momentum
+
+    @property
+    def dipole_moment(self):
+        return self._basis_set.dipole_moment
+
+    @property
+    def spf(self):
+        return self._basis_set.spf
+
+    @property
+    def bra_spf(self):
+        return self._basis_set.bra_spf
+
+    @property
+    def nuclear_repulsion_energy(self):
+        return self._basis_set.nuclear_repulsion_energy
+
+    @property
+    def particle_charge(self):
+        return self._basis_set.particle_charge
+
+    # time-dependent operators (system.py:144-215)
+    def set_time_evolution_operator(self, time_evolution_operator, add_h_0=True, add_u_0=True):
+        if not isinstance(time_evolution_operator, typing.Iterable):
+            time_evolution_operator = [time_evolution_operator]
+        self._add_h_0 = add_h_0
+        self._add_u_0 = add_u_0
+        self._time_evolution_operator = [op.set_system(self) for op in time_evolution_operator]
+
+    @property
+    def has_one_body_time_evolution_operator(self):
+        return any(op.is_one_body_operator for op in self._time_evolution_operator)
+
+    @property
+    def has_two_body_time_evolution_operator(self):
+        return any(op.is_two_body_operator for op in self._time_evolution_operator)
+
+    def h_t(self, current_time):
+        h_0 = self._basis_set.h if self._add_h_0 else self.np.zeros_like(self._basis_set.h)
+        if not self.has_one_body_time_evolution_operator:
+            return h_0
+        return h_0 + sum(op.h_t(current_time) for op in self._time_evolution_operator)
+
+    def u_t(self, current_time):
+        u_0 = self._basis_set.u if self._add_u_0 else self.np.zeros_like(self._basis_set.u)
+        if not self.has_two_body_time_evolution_operator:
+            return u_0
+        return u_0 + sum(op.u_t(current_time) for op in self._time_evolution_operator)
+
+    def transform_one_body_elements(self, h, C, C_tilde=None):
+        return self._basis_set.transform_one_body_elements(h, C, np=self.np, C_tilde=C_tilde)
+
+    def transform_two_body_elements(self, u, C, C_tilde=None):
+        return self._basis_set.transform_two_body_elements(u, C, np=self.np, C_tilde=C_tilde)
+
+    def copy_system(self):
+        """Deep copy of the system; array modules are shared (system.py:227-250)."""
+        memo = {id(self.np): self.np, id(self._basis_set.np): self._basis_set.np}
+        for holder in (self, self._basis_set, getattr(self._basis_set, "potential", None)):
+            if holder is None:
+                continue
+            for value in vars(holder).values():
+                if isinstance(value, types.ModuleType):
+                    memo[id(value)] = value
+        new_system = copy.deepcopy(self, memo)
+        assert new_system.np is self.np
+        return new_system
+
+    # helpers shared by the concrete systems -----------------------------------------------
+    def _occupied_trace_terms(self, h, u):
+        """``tr h[o,o]``, ``sum_ij u[i,j,i,j]``, ``sum_ij u[i,j,j,i]`` on the n_occ^4 corner (tiny)."""
+        np = self.np
+        o = self.o
+        h_oo = h[o, o]
+        u_oooo = u[o, o, o, o]
+        direct = np.trace(np.trace(u_oooo, axis1=1, axis2=3))
+        exchange = np.trace(np.trace(u_oooo, axis1=1, axis2=2))
+        return np.trace(h_oo), direct, exchange
