@@ -62,22 +62,37 @@ def transform_flops(n, m=None):
 def workload_n(args):
     if args.n:
         return args.n
-    return N_BY_GPUS.get(args.gpus, int(round(128 * args.gpus**0.2 / args.gpus)) * args.gpus)
+    gpus = max(args.gpus, 1)
+    return N_BY_GPUS.get(gpus, int(round(128 * gpus**0.2 / gpus)) * gpus)
 
 
-def make_inputs(n, seed=2):
+def make_inputs(n, seed=2, with_u=True):
     """configs[1] inputs on the host: u ~ N(0,1) with u_pqrs = u_qpsr, symmetric h,
     s = I, C = qr(N(0,1))."""
     import numpy as np
 
     rng = np.random.default_rng(seed)
-    u = rng.standard_normal((n, n, n, n))
-    u = 0.5 * (u + u.transpose(1, 0, 3, 2))
+    out = {}
+    if with_u:
+        u = rng.standard_normal((n, n, n, n))
+        out["u"] = 0.5 * (u + u.transpose(1, 0, 3, 2))
+    rng = np.random.default_rng(seed + 1000)
     h = rng.standard_normal((n, n))
-    h = 0.5 * (h + h.T)
-    s = np.eye(n)
-    C = np.linalg.qr(rng.standard_normal((n, n)))[0]
-    return {"u": u, "h": h, "s": s, "C": np.ascontiguousarray(C)}
+    out["h"] = 0.5 * (h + h.T)
+    out["s"] = np.eye(n)
+    out["C"] = np.ascontiguousarray(np.linalg.qr(rng.standard_normal((n, n)))[0])
+    return out
+
+
+def make_u_planes(n, p0, p1, seed=2):
+    """Planes [p0, p1) of a sharded synthetic u: every plane has its own seeded stream, so any rank can
+    generate exactly its slab (no rank ever holds the whole tensor)."""
+    import numpy as np
+
+    out = np.empty((p1 - p0, n, n, n))
+    for p in range(p0, p1):
+        out[p - p0] = np.random.default_rng([seed, p]).standard_normal((n, n, n))
+    return out
 
 
 def host_threads():
@@ -250,7 +265,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    inputs = make_inputs(n)
+    inputs = make_inputs(n, with_u=(world == 1))
     peak_tflops = ops.probe_dmma_tflops()
 
     # ---- leg 1: inputs resident in HBM -----------------------------------------------------------
@@ -264,7 +279,10 @@ def run_ours(args):
     else:
         from quantum_systems_b200 import sharded
 
-        basis = sharded.ShardedBasisSet.from_global(n, inputs["h"], inputs["s"], inputs["u"], rank, world)
+        ctx = sharded.ProcessContext()
+        basis = sharded.ShardedBasisSet.from_slabs(
+            ctx, n, inputs["h"], inputs["s"], lambda p0, p1: make_u_planes(n, p0, p1)
+        )
         C_dev = xp.asarray(inputs["C"])
 
         def step():
@@ -325,9 +343,41 @@ def run_ours(args):
         }
         del host_basis
     elif world > 1 and not args.no_e2e:
-        e2e = basis.e2e_leg(inputs, args, flops) if hasattr(basis, "e2e_leg") else None
+        # every rank keeps its slab of u in pinned host memory: H2D of the slab, sharded change_basis (peer
+        # stores over NVLink), D2H of the slab of the result
+        p0, p1 = basis.u.planes(rank)
+        host_in = torch.empty((p1 - p0, n, n, n), dtype=torch.float64, pin_memory=True)
+        host_in.copy_(basis.u.local())
+        host_out = torch.empty_like(host_in, pin_memory=True)
+        h_host = torch.empty((n, n), dtype=torch.float64, pin_memory=True).copy_(basis.h)
+        e2e_steps = min(args.steps, 10)
+
+        def e2e_step():
+            basis.u.local().copy_(host_in, non_blocking=True)
+            basis.h.copy_(h_host, non_blocking=True)
+            basis.change_basis(C_dev)
+            host_out.copy_(basis.u.local(), non_blocking=True)
+            h_host.copy_(basis.h, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+        slab_bytes = max_over_ranks(float(host_in.numel() * 8))
+        e2e = {
+            "value": flops / e2e_s * 1e-12, "unit": UNIT, "h2d_bytes_per_step": int(slab_bytes) + n * n * 8,
+            "d2h_bytes_per_step": int(slab_bytes) + n * n * 8, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+            "api": "per rank: pinned host slab -> ShardedBasisSet.change_basis(C) -> pinned host slab",
+        }
     clocks = sampler.stop() if rank == 0 else None
 
+    if world > 1:
+        ctx.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -75,6 +75,33 @@ int qs_quarter_transform(const void* A, int a_dtype, int64_t X, int64_t K, int64
                          int64_t sx0, int64_t sx1, int64_t w_inner, int64_t sw0, int64_t sw1,
                          void* stream);
 
+/* Scattering variant: the fused re-partition of the sharded schedule.  The new index w selects
+ * the destination buffer host_out_table[w / w_inner] (n_dest device pointers held in a HOST array;
+ * peers' buffers mapped with qs_ipc_open) and is stored at (w % w_inner) * sw0 inside it.  The row
+ * index is split three ways, x = (x2 * x_mid + x1) * x_inner + x0, and contributes
+ * x2 * sx2 + x1 * sx1 + x0 * sx0, so a shard's planes land between the planes of the other ranks.
+ * One launch computes the quarter step AND delivers every tile to the GPU that owns it over
+ * NVLink -- the all-to-all of SURVEY.md section 8e without a second pass over memory. */
+int qs_quarter_transform_scatter(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda,
+                                 const void* image, int m_dtype, int64_t W,
+                                 void* const* host_out_table, int64_t n_dest, int64_t x_inner,
+                                 int64_t x_mid, int64_t sx0, int64_t sx1, int64_t sx2,
+                                 int64_t w_inner, int64_t sw0, void* stream);
+
+/* Copy `rows` rows of n elements into rows of `pitch` >= n elements, zero-filling the tail (real
+ * tensors with odd n need an even pitch before they can be described to TMA). */
+int qs_pad_rows(const void* in, void* out, int64_t rows, int64_t n, int64_t pitch, int dtype,
+                void* stream);
+
+/* Peer-memory plumbing for the scattering store: cudaMalloc + CUDA IPC export / open / close / free.
+ * host_handle points at qs_ipc_handle_bytes() bytes of host memory (exchanged between the ranks by
+ * the caller, e.g. torch.distributed.all_gather_object). */
+int qs_ipc_handle_bytes(void);
+int qs_ipc_alloc(int64_t bytes, void** dev_ptr, void* host_handle);
+int qs_ipc_open(const void* host_handle, void** dev_ptr);
+int qs_ipc_close(void* dev_ptr);
+int qs_ipc_free(void* dev_ptr);
+
 /* ---------------------------------------------------------------------------------------------
  * One-body transform  h' = Ct (h C)   replaces BasisSet.transform_one_body_elements
  * (basis_set.py:329-334).  h: (n, n); C: (n, n_new); Ct: (n_new, n) or NULL; out: (n_new, n_new).
@@ -123,6 +150,11 @@ int qs_fock_general(const void* h, int h_dtype, const void* u, int u_dtype, int6
                     int64_t n_occ, void* f, int64_t p_begin, int64_t p_end, void* stream);
 int qs_fock_spatial(const void* h, int h_dtype, const void* u, int u_dtype, int64_t n,
                     int64_t n_occ, void* f, int64_t p_begin, int64_t p_end, void* stream);
+/* General Fock matrix from a tensor sharded on its THIRD index (what a sharded change_basis leaves):
+ * u_cols = u[:, :, q_begin:q_end, :] stored dense as (n, n, q_end-q_begin, n); writes columns
+ * [q_begin, q_end) of f (h, f full (n, n) matrices). */
+int qs_fock_general_cols(const void* h, int h_dtype, const void* u_cols, int u_dtype, int64_t n,
+                         int64_t n_occ, void* f, int64_t q_begin, int64_t q_end, void* stream);
 /* Same reductions on pre-gathered (n_occ, n, n) blocks direct[i,p,q] = u[p,i,q,i] and (optional,
  * may be NULL) exchange[i,p,q] = u[p,i,i,q]:  f = h + scale_direct * sum_i direct + scale_exchange *
  * sum_i exchange.  Used when u lives in host memory and only the needed elements are staged. */

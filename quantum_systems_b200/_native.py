@@ -29,6 +29,13 @@ SIGNATURES = {
     "qs_coeff_image_bytes": [_i64, _i64, _int, _int, ctypes.POINTER(_i64)],
     "qs_build_coeff_image": [_ptr, _int, _i64, _i64, _int, _i64, _i64, _int, _ptr, _ptr],
     "qs_quarter_transform": [_ptr, _int, _i64, _i64, _i64, _ptr, _int, _i64, _ptr, _i64, _i64, _i64, _i64, _i64, _i64, _ptr],
+    "qs_quarter_transform_scatter": [_ptr, _int, _i64, _i64, _i64, _ptr, _int, _i64, ctypes.POINTER(_ptr), _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _ptr],
+    "qs_pad_rows": [_ptr, _ptr, _i64, _i64, _i64, _int, _ptr],
+    "qs_ipc_handle_bytes": [],
+    "qs_ipc_alloc": [_i64, ctypes.POINTER(_ptr), _ptr],
+    "qs_ipc_open": [_ptr, ctypes.POINTER(_ptr)],
+    "qs_ipc_close": [_ptr],
+    "qs_ipc_free": [_ptr],
     "qs_transform_one_body_workspace_bytes": [_i64, _i64, _int, _int, ctypes.POINTER(_i64)],
     "qs_transform_one_body": [_ptr, _int, _ptr, _ptr, _int, _i64, _i64, _ptr, _ptr, _ptr],
     "qs_add_spin_two_body": [_ptr, _int, _i64, _ptr, _int, _int, _i64, _i64, _ptr],
@@ -37,6 +44,7 @@ SIGNATURES = {
     "qs_spin_squared_two_body": [_ptr, _ptr, _ptr, _i64, _int, _ptr, _i64, _i64, _ptr],
     "qs_fock_gathered": [_ptr, _int, _ptr, _ptr, _int, _i64, _i64, _dbl, _dbl, _ptr, _ptr],
     "qs_fock_general": [_ptr, _int, _ptr, _int, _i64, _i64, _ptr, _i64, _i64, _ptr],
+    "qs_fock_general_cols": [_ptr, _int, _ptr, _int, _i64, _i64, _ptr, _i64, _i64, _ptr],
     "qs_fock_spatial": [_ptr, _int, _ptr, _int, _i64, _i64, _ptr, _i64, _i64, _ptr],
     "qs_odqd_coulomb_workspace_bytes": [_i64, _i64, ctypes.POINTER(_i64)],
     "qs_odqd_coulomb": [_ptr, _ptr, _dbl, _dbl, _i64, _i64, _ptr, _ptr, _i64, _ptr],

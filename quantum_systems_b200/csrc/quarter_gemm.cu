@@ -29,9 +29,15 @@ constexpr int kConsumerWarps = 4;
 constexpr int kThreads = kConsumerWarps * 32;
 constexpr int kATileBytes = kBlockX * kChunkK * 8;  // 16 KiB
 
+constexpr int kMaxDest = 16;    // destination buffers of a scattering store (ranks of one NVSwitch domain)
+
 struct QuarterParams {
     const double* image;      // [tiles_w][nchunks][2][NT][32][2] doubles (this launch's tile group)
     double* out;
+    // Scattering store (fused re-partition): when ndest > 0 the new index w selects the destination
+    // buffer outs[w / w_inner] -- a peer GPU's memory mapped over NVLink -- and sw1 is unused.
+    double* outs[kMaxDest];
+    int ndest;
     uint32_t X;               // rows of A
     uint32_t Wp;              // real columns actually valid (W or 2W)
     uint32_t w_first;         // first real column of this launch's tile group
@@ -40,10 +46,10 @@ struct QuarterParams {
     int last_halves;          // 8-k' halves of the last chunk that hold data (1 or 2)
     int tiles_w;              // column tiles in this group, each 8*NT wide
     long long stagger_clocks; // start delay of the second CTA wave (0 = none)
-    // store address = (w/w_inner)*sw1 + (w%w_inner)*sw0 + (x/x_inner)*sx1 + (x%x_inner)*sx0
-    // in OUTPUT ELEMENTS (w = w' for real output, w'/2 for complex output)
-    uint32_t x_inner, w_inner;
-    long long sx0, sx1, sw0, sw1;
+    // store address = (w/w_inner)*sw1 + (w%w_inner)*sw0 + x2*sx2 + x1*sx1 + x0*sx0 with
+    // x = (x2 * x_mid + x1) * x_inner + x0, in OUTPUT ELEMENTS (w = w' for real output, w'/2 for complex)
+    uint32_t x_inner, x_mid, w_inner;
+    long long sx0, sx1, sx2, sw0, sw1;
 };
 
 __device__ __forceinline__ int row_permutation(int g) {
@@ -54,7 +60,7 @@ __device__ __forceinline__ int row_permutation(int g) {
 
 template <int NT, bool COMPLEX_OUT>
 __global__ void __launch_bounds__(kThreads, 2)
-quarter_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const QuarterParams p) {
+quarter_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ QuarterParams p) {
     constexpr int kBTileBytes = NT * 1024;  // 16 k' x 8*NT w' doubles
     constexpr int kStageBytes = kATileBytes + kBTileBytes;
 
@@ -175,7 +181,9 @@ quarter_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const QuarterPara
             xok[mt] = x < p.X;
             const uint32_t xq = x / p.x_inner;
             const uint32_t xr = x - xq * p.x_inner;
-            xoff[mt] = (long long)xq * p.sx1 + (long long)xr * p.sx0;
+            const uint32_t x2 = xq / p.x_mid;
+            const uint32_t x1 = xq - x2 * p.x_mid;
+            xoff[mt] = (long long)x2 * p.sx2 + (long long)x1 * p.sx1 + (long long)xr * p.sx0;
         }
         const uint32_t wbase = p.w_first + tile_w * (8 * NT);
 #pragma unroll
@@ -187,10 +195,11 @@ quarter_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const QuarterPara
                     const uint32_t wq = w / p.w_inner;
                     const uint32_t wr = w - wq * p.w_inner;
                     const long long woff = (long long)wq * p.sw1 + (long long)wr * p.sw0;
+                    double* const base = p.ndest ? p.outs[wq] : p.out;
 #pragma unroll
                     for (int mt = 0; mt < 4; ++mt)
                         if (xok[mt])
-                            *reinterpret_cast<double2*>(p.out + 2 * (woff + xoff[mt])) =
+                            *reinterpret_cast<double2*>(base + 2 * (woff + xoff[mt])) =
                                 make_double2(acc[mt][nt][0], acc[mt][nt][1]);
                 }
             } else {
@@ -201,9 +210,10 @@ quarter_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const QuarterPara
                         const uint32_t wq = w / p.w_inner;
                         const uint32_t wr = w - wq * p.w_inner;
                         const long long woff = (long long)wq * p.sw1 + (long long)wr * p.sw0;
+                        double* const base = p.ndest ? p.outs[wq] : p.out;
 #pragma unroll
                         for (int mt = 0; mt < 4; ++mt)
-                            if (xok[mt]) p.out[woff + xoff[mt]] = acc[mt][nt][e];
+                            if (xok[mt]) base[woff + xoff[mt]] = acc[mt][nt][e];
                     }
                 }
             }
@@ -427,22 +437,34 @@ int qs_build_coulomb_image(const double* grid, double alpha, double a, int64_t G
     return build_image(q, tl, image, stream);
 }
 
-extern "C" int qs_quarter_transform(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda, const void* image,
-                                    int m_dtype, int64_t W, void* out, int64_t x_inner, int64_t sx0, int64_t sx1,
-                                    int64_t w_inner, int64_t sw0, int64_t sw1, void* stream) {
-    QS_REQUIRE(A && image && out, "qs_quarter_transform: null pointer");
+namespace {
+
+int quarter_launch(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda, const void* image, int m_dtype,
+                   int64_t W, void* out, void* const* out_table, int64_t n_dest, int64_t x_inner, int64_t x_mid,
+                   int64_t sx0, int64_t sx1, int64_t sx2, int64_t w_inner, int64_t sw0, int64_t sw1, void* stream) {
+    QS_REQUIRE(A && image && (out || out_table), "qs_quarter_transform: null pointer");
     QS_REQUIRE(X > 0 && K > 0 && W > 0 && lda >= K, "qs_quarter_transform: bad extents");
     QS_REQUIRE(X < (1LL << 31) - kBlockX, "qs_quarter_transform: X=%lld exceeds 2^31", (long long)X);
-    QS_REQUIRE(x_inner > 0 && w_inner > 0 && x_inner < (1LL << 32) && w_inner < (1LL << 31),
+    QS_REQUIRE(x_inner > 0 && w_inner > 0 && x_inner < (1LL << 32) && w_inner < (1LL << 31) && x_mid > 0 &&
+                   x_mid < (1LL << 32),
                "qs_quarter_transform: bad inner extents");
+    QS_REQUIRE(n_dest >= 0 && n_dest <= kMaxDest, "qs_quarter_transform_scatter: at most %d destinations", kMaxDest);
+    QS_REQUIRE(n_dest == 0 || qs_ceil_div(W, w_inner) <= n_dest,
+               "qs_quarter_transform_scatter: W=%lld needs more than %lld destinations of %lld", (long long)W,
+               (long long)n_dest, (long long)w_inner);
     const Tiling tl = make_tiling(K, W, a_dtype, m_dtype);
     const bool out_complex = a_dtype == QS_C128 || m_dtype == QS_C128;
     const int64_t pitch_bytes = lda * 8 * qs_elem_doubles(a_dtype);
     QS_REQUIRE(pitch_bytes % 16 == 0,
                "qs_quarter_transform: row pitch of A must be a multiple of 16 bytes (pad odd real K)");
+    // A and the image are TMA / bulk-copy sources (16 bytes); the epilogue stores whole elements
+    const uintptr_t out_mask = out_complex ? 15 : 7;
     QS_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(image) & 15) == 0 &&
-                   (reinterpret_cast<uintptr_t>(out) & 15) == 0,
-               "qs_quarter_transform: pointers must be 16-byte aligned");
+                   (reinterpret_cast<uintptr_t>(out) & out_mask) == 0,
+               "qs_quarter_transform: A and image must be 16-byte aligned, out element-aligned");
+    for (int64_t d = 0; d < n_dest; ++d)
+        QS_REQUIRE(out_table[d] && (reinterpret_cast<uintptr_t>(out_table[d]) & out_mask) == 0,
+                   "qs_quarter_transform_scatter: destination %lld is null or misaligned", (long long)d);
 
     EncodeTiledFn encode = get_encode_fn();
     QS_REQUIRE(encode, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
@@ -466,8 +488,11 @@ extern "C" int qs_quarter_transform(const void* A, int a_dtype, int64_t X, int64
     for (int gi = 0; gi < tl.ngroups; ++gi) {
         const TileGroup& gr = tl.group[gi];
         QuarterParams p;
+        memset(&p, 0, sizeof(p));
         p.image = static_cast<const double*>(image) + gr.image_offset;
         p.out = static_cast<double*>(out);
+        p.ndest = (int)n_dest;
+        for (int64_t d = 0; d < n_dest; ++d) p.outs[d] = static_cast<double*>(out_table[d]);
         p.X = (uint32_t)X;
         p.Wp = (uint32_t)tl.Wp;
         p.w_first = (uint32_t)gr.w_first;
@@ -477,15 +502,35 @@ extern "C" int qs_quarter_transform(const void* A, int a_dtype, int64_t X, int64
         p.tiles_w = gr.tiles_w;
         p.stagger_clocks = 0;
         p.x_inner = (uint32_t)x_inner;
+        p.x_mid = (uint32_t)x_mid;
         p.w_inner = (uint32_t)w_inner;
         p.sx0 = sx0;
         p.sx1 = sx1;
+        p.sx2 = sx2;
         p.sw0 = sw0;
-        p.sw1 = sw1;
+        p.sw1 = n_dest ? 0 : sw1;
         QS_REQUIRE((int64_t)p.tiles_x * p.tiles_w < (1LL << 31), "qs_quarter_transform: too many tiles");
         const int rc = out_complex ? launch_nt<true>(gr.NT, map, p, st) : launch_nt<false>(gr.NT, map, p, st);
         if (rc) return rc;
     }
     qs_timing_end(span, stream);
     return QS_OK;
+}
+
+}  // namespace
+
+extern "C" int qs_quarter_transform(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda, const void* image,
+                                    int m_dtype, int64_t W, void* out, int64_t x_inner, int64_t sx0, int64_t sx1,
+                                    int64_t w_inner, int64_t sw0, int64_t sw1, void* stream) {
+    return quarter_launch(A, a_dtype, X, K, lda, image, m_dtype, W, out, nullptr, 0, x_inner, 0xFFFFFFFFLL, sx0, sx1, 0,
+                          w_inner, sw0, sw1, stream);
+}
+
+extern "C" int qs_quarter_transform_scatter(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda,
+                                            const void* image, int m_dtype, int64_t W, void* const* host_out_table,
+                                            int64_t n_dest, int64_t x_inner, int64_t x_mid, int64_t sx0, int64_t sx1,
+                                            int64_t sx2, int64_t w_inner, int64_t sw0, void* stream) {
+    QS_REQUIRE(host_out_table && n_dest > 0, "qs_quarter_transform_scatter: empty destination table");
+    return quarter_launch(A, a_dtype, X, K, lda, image, m_dtype, W, nullptr, host_out_table, n_dest, x_inner, x_mid, sx0,
+                          sx1, sx2, w_inner, sw0, 0, stream);
 }

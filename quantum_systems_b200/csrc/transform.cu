@@ -76,6 +76,12 @@ int rotated_quarter(const void* A, int a_dtype, int64_t X, int64_t K, int64_t ld
 
 }  // namespace
 
+extern "C" int qs_pad_rows(const void* in, void* out, int64_t rows, int64_t n, int64_t pitch, int dtype, void* stream) {
+    QS_REQUIRE(in && out && rows > 0 && n > 0 && pitch >= n, "qs_pad_rows: bad arguments");
+    const int64_t d = qs_elem_doubles(dtype);  // complex rows are rows of 2n doubles
+    return pad_rows(in, out, rows, n * d, pitch * d, stream);
+}
+
 extern "C" int qs_transform_two_body_workspace_bytes(int64_t n, int64_t n_new, int u_dtype, int c_dtype,
                                                      int64_t* bytes) {
     QS_REQUIRE(n > 0 && n_new > 0 && bytes, "qs_transform_two_body_workspace_bytes: bad arguments");

@@ -1,0 +1,587 @@
+"""Sharded two-body pipeline: one tensor ``u`` spread over the GPUs of an NVSwitch domain.
+
+Once ``u`` no longer fits one GPU (n >~ 300 spin-orbitals) it is block-partitioned on its LEADING
+index, ``ceil(n / W)`` planes per rank.  The four-index transform of
+``BasisSet.transform_two_body_elements`` (reference basis_set.py:336-350) then runs as
+
+    u[a_loc,b,c,d] --C--> T1[s,a_loc,b,c] --C--> T2[r,s,a_loc,b]      steps 1-2: local contractions
+                                              \\=> T2[r_loc,s,a,b]     re-partition a -> r (exchange)
+    T2[r_loc,s,a,b] --C~--> T3[q,r_loc,s,a] --C~--> u'[p,q,r_loc,s]   steps 3-4: local contractions
+                                              \\=> u'[p_loc,q,r,s]     re-partition r -> p (exchange)
+
+like the transpose steps of a distributed FFT.  Both exchanges are FUSED into the producing GEMM: the
+epilogue of steps 2 and 4 stores every tile straight into the buffer of the rank that owns it, through
+peer pointers mapped with CUDA IPC over NVLink (``qs_quarter_transform_scatter``), so no tile is
+written locally, re-read and sent.  ``torch.distributed`` is used for the rendezvous (exchange of IPC
+handles), for stream-ordered barriers and for the tiny all-gather of the Fock matrix; it never
+carries tensor data on this path.  ``exchange="collective"`` selects the plain
+``all_to_all_single`` schedule instead (validation, and CPU/gloo tests of the partition logic).
+
+One process per GPU drives one rank (``ProcessContext``).  ``EmulatedContext`` drives all W ranks
+from one process on one device; it exists to test the schedule and the scattering kernel on a
+single GPU.
+
+The arithmetic runs in the ``engine``: ``CudaEngine`` (the kernels of ``libqsb200.so``) is the only
+engine this package provides -- there is no CPU fallback.  Tests inject their own numpy engine to
+check the schedule under gloo without a GPU.
+"""
+
+import ctypes
+
+import torch
+
+from . import _native
+from ._native import QS_C128, QS_F64
+
+_CODES = {torch.float64: QS_F64, torch.complex128: QS_C128}
+_ITEMSIZE = {torch.float64: 8, torch.complex128: 16}
+
+
+def block_partition(n, world):
+    """Contiguous blocks of ``ceil(n / world)`` indices; trailing ranks may be short or empty.
+    Returns ``(block, offsets)`` with rank r owning ``[offsets[r], offsets[r + 1])``."""
+    block = -(-n // world)
+    return block, [min(r * block, n) for r in range(world + 1)]
+
+
+def padded_pitch(n, dtype):
+    """Row pitch (elements) of a contracted axis of extent n: real rows must be a multiple of 16 bytes
+    to be described to TMA (csrc/transform.cu)."""
+    return n if dtype == torch.complex128 else n + (n & 1)
+
+
+# ------------------------------------------------------------------------------------------------
+# engine: where the arithmetic runs
+# ------------------------------------------------------------------------------------------------
+class DeviceBuffer:
+    """A flat device allocation of ``numel`` elements of ``dtype``: either a torch tensor (scratch from
+    the caching allocator) or a raw pointer (an IPC-exported cudaMalloc block or a peer's mapping)."""
+
+    def __init__(self, ptr, numel, dtype, tensor=None):
+        self.ptr = int(ptr)
+        self.numel = int(numel)
+        self.dtype = dtype
+        self.tensor = tensor
+
+    def at(self, offset):
+        return self.ptr + int(offset) * _ITEMSIZE[self.dtype]
+
+    def as_tensor(self):
+        """torch view of the buffer (local memory only)."""
+        if self.tensor is None:
+            self.tensor = torch.as_tensor(_CudaArray(self.ptr, self.numel, self.dtype), device="cuda")
+        return self.tensor
+
+
+class _CudaArray:
+    def __init__(self, ptr, numel, dtype):
+        self.__cuda_array_interface__ = {
+            "shape": (numel,),
+            "typestr": "<c16" if dtype == torch.complex128 else "<f8",
+            "data": (ptr, False),
+            "version": 3,
+            "strides": None,
+        }
+
+
+class CudaEngine:
+    """Quarter GEMMs of libqsb200.so on the current CUDA stream."""
+
+    def empty(self, numel, dtype):
+        t = torch.empty(max(int(numel), 1), dtype=dtype, device="cuda")
+        return DeviceBuffer(t.data_ptr(), numel, dtype, tensor=t)
+
+    @staticmethod
+    def _stream():
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def asarray(self, a, dtype=None):
+        from . import _arrays
+
+        return _arrays.to_device(a, dtype)
+
+    def image(self, M, K, W, a_dtype, stride_k, stride_w, conj=False):
+        from . import ops
+
+        return ops.coeff_image(M, K, W, a_dtype, stride_k, stride_w, conj=conj)
+
+    def pad_rows(self, src, rows, n, pitch, dst):
+        _native.call(
+            "qs_pad_rows", ctypes.c_void_p(src.at(0)), ctypes.c_void_p(dst.at(0)), rows, n, pitch, _CODES[src.dtype],
+            self._stream(),
+        )
+
+    def quarter(self, A, X, K, lda, image, m_dtype, W, out, out_offset, x_inner, sx0, sx1, w_inner, sw0, sw1):
+        if X <= 0:
+            return
+        _native.call(
+            "qs_quarter_transform", ctypes.c_void_p(A.at(0)), _CODES[A.dtype], X, K, lda,
+            ctypes.c_void_p(image.data_ptr()), _CODES[m_dtype], W, ctypes.c_void_p(out.at(out_offset)), x_inner, sx0,
+            sx1, w_inner, sw0, sw1, self._stream(),
+        )
+
+    def quarter_scatter(self, A, X, K, lda, image, m_dtype, W, dests, x_inner, x_mid, sx0, sx1, sx2, w_inner, sw0):
+        if X <= 0:
+            return
+        table = (ctypes.c_void_p * len(dests))(*[buf.at(off) for buf, off in dests])
+        _native.call(
+            "qs_quarter_transform_scatter", ctypes.c_void_p(A.at(0)), _CODES[A.dtype], X, K, lda,
+            ctypes.c_void_p(image.data_ptr()), _CODES[m_dtype], W, table, len(dests), x_inner, max(x_mid, 1), sx0, sx1,
+            sx2, w_inner, sw0, self._stream(),
+        )
+
+
+# ------------------------------------------------------------------------------------------------
+# contexts: who drives which rank, and how ranks reach each other's memory
+# ------------------------------------------------------------------------------------------------
+class EmulatedContext:
+    """All ``world`` ranks driven by this process on the current device (single-GPU tests)."""
+
+    def __init__(self, world, engine=None):
+        self.world = world
+        self.local_ranks = list(range(world))
+        self.engine = engine if engine is not None else CudaEngine()
+        self.exchange = "peer"
+
+    def shared_empty(self, numels, dtype):
+        """One buffer per rank, visible to every rank.  Returns ``{rank: [buffer of rank 0, ...]}``."""
+        buffers = [self.engine.empty(numels[r], dtype) for r in range(self.world)]
+        return {r: buffers for r in self.local_ranks}
+
+    def shared_cached(self, tag, numels, dtype):
+        return _cached(self, tag, numels, dtype)
+
+    def barrier(self):
+        pass  # one stream, program order
+
+
+class ProcessContext:
+    """This process drives one rank of an initialised ``torch.distributed`` group (one process per GPU).
+
+    ``exchange="peer"`` (default on CUDA): destination buffers are cudaMalloc blocks exported with CUDA
+    IPC and opened by every peer; the GEMM epilogues store into them over NVLink.
+    ``exchange="collective"``: ``all_to_all_single`` of a locally written send buffer.
+    """
+
+    def __init__(self, group=None, engine=None, exchange=None):
+        import torch.distributed as dist
+
+        if not dist.is_initialized():
+            raise RuntimeError("ProcessContext needs an initialised torch.distributed process group")
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.local_ranks = [self.rank]
+        self.engine = engine if engine is not None else CudaEngine()
+        self.on_cuda = isinstance(self.engine, CudaEngine)
+        self.exchange = exchange or ("peer" if self.on_cuda else "collective")
+        self._flag = None
+        self._allocations = []  # (local pointer, [opened peer pointers]) for close()
+
+    def barrier(self):
+        """Stream-ordered barrier: a one-element all-reduce on the current stream (no host block)."""
+        if self._flag is None:
+            self._flag = torch.zeros(1, dtype=torch.float32, device="cuda" if self.on_cuda else "cpu")
+        self.dist.all_reduce(self._flag, op=self.dist.ReduceOp.MAX, group=self.group)
+
+    def shared_empty(self, numels, dtype):
+        if self.exchange != "peer":
+            raise RuntimeError("shared buffers exist only for exchange='peer'")
+        hb = _native.load().qs_ipc_handle_bytes()
+        handle = ctypes.create_string_buffer(hb)
+        local = ctypes.c_void_p()
+        nbytes = max(int(numels[self.rank]), 1) * _ITEMSIZE[dtype]
+        _native.call("qs_ipc_alloc", nbytes, ctypes.byref(local), handle)
+        handles = [None] * self.world
+        self.dist.all_gather_object(handles, handle.raw, group=self.group)
+        buffers, opened = [], []
+        for r in range(self.world):
+            if r == self.rank:
+                buffers.append(DeviceBuffer(local.value, numels[r], dtype))
+            else:
+                peer = ctypes.c_void_p()
+                _native.call("qs_ipc_open", ctypes.c_char_p(handles[r]), ctypes.byref(peer))
+                opened.append(peer.value)
+                buffers.append(DeviceBuffer(peer.value, numels[r], dtype))
+        self._allocations.append((local.value, opened))
+        return {self.rank: buffers}
+
+    def shared_cached(self, tag, numels, dtype):
+        """Peer-visible scratch that persists across calls (the IPC rendezvous is paid once)."""
+        return _cached(self, tag, numels, dtype)
+
+    def close(self):
+        """Unmap the peers' buffers and free the local ones (collective: every rank must call it)."""
+        if self.on_cuda:
+            torch.cuda.synchronize()
+        self.barrier()
+        for local, opened in self._allocations:
+            for ptr in opened:
+                _native.call("qs_ipc_close", ctypes.c_void_p(ptr))
+        if self.on_cuda:
+            torch.cuda.synchronize()
+        self.barrier()
+        if self.on_cuda:
+            torch.cuda.synchronize()
+        for local, _ in self._allocations:
+            _native.call("qs_ipc_free", ctypes.c_void_p(local))
+        self._allocations = []
+
+    # collective exchange (validation path)
+    def all_to_all(self, send, send_splits, recv, recv_splits):
+        """``all_to_all_single`` on flat float64 views (complex buffers are pairs of doubles)."""
+        s, r = send.as_tensor(), recv.as_tensor()
+        scale = 1
+        if s.is_complex():
+            s, r = torch.view_as_real(s).reshape(-1), torch.view_as_real(r).reshape(-1)
+            scale = 2
+        self.dist.all_to_all_single(
+            r[: scale * sum(recv_splits)], s[: scale * sum(send_splits)], [scale * x for x in recv_splits],
+            [scale * x for x in send_splits], group=self.group,
+        )
+
+
+def _cached(ctx, tag, numels, dtype):
+    cache = ctx.__dict__.setdefault("_shared_cache", {})
+    key = (tag, tuple(int(x) for x in numels), dtype)
+    if key not in cache:
+        cache[key] = ctx.shared_empty(numels, dtype)
+    return cache[key]
+
+
+# ------------------------------------------------------------------------------------------------
+# the sharded tensor handle
+# ------------------------------------------------------------------------------------------------
+class ShardedTwoBody:
+    """``u`` of shape ``(n, n, n, n)`` block-partitioned on its leading index.
+
+    ``local[r]`` is rank r's ``(planes_r, n, n, n)`` slab (only the ranks this process drives).  The
+    slabs live in peer-visible buffers; ``spare`` is the second set the next transform writes into
+    (ping-pong: a transform recycles the buffers of the tensor it replaced one call earlier).
+    """
+
+    def __init__(self, ctx, n, dtype, buffers, spare=None):
+        self.ctx = ctx
+        self.n = n
+        self.dtype = dtype
+        self.buffers = buffers  # {rank: [buffer of every rank]}
+        self.spare = spare
+        self.block, self.offsets = block_partition(n, ctx.world)
+
+    @property
+    def shape(self):
+        return (self.n,) * 4
+
+    def planes(self, rank):
+        return self.offsets[rank], self.offsets[rank + 1]
+
+    def local(self, rank=None):
+        rank = self.ctx.local_ranks[0] if rank is None else rank
+        p0, p1 = self.planes(rank)
+        n = self.n
+        flat = self.buffers[rank][rank].as_tensor()
+        return flat[: (p1 - p0) * n**3].view(p1 - p0, n, n, n)
+
+    @classmethod
+    def empty(cls, ctx, n, dtype, with_spare=True):
+        _, offsets = block_partition(n, ctx.world)
+        numels = [(offsets[r + 1] - offsets[r]) * n**3 for r in range(ctx.world)]
+        if ctx.exchange == "peer":
+            buffers = ctx.shared_empty(numels, dtype)
+            spare = ctx.shared_empty(numels, dtype) if with_spare else None
+        else:
+            buffers = {r: {r: ctx.engine.empty(numels[r], dtype)} for r in ctx.local_ranks}
+            spare = None
+        return cls(ctx, n, dtype, buffers, spare)
+
+    def gather(self):
+        """The full tensor on every rank (small n only: tests, inspection)."""
+        ctx = self.ctx
+        if isinstance(ctx, EmulatedContext):
+            return torch.cat([self.local(r) for r in range(ctx.world)], dim=0)
+        local = self.local()
+        n = self.n
+        padded = torch.zeros((self.block, n, n, n), dtype=local.dtype, device=local.device)
+        padded[: local.shape[0]] = local
+        parts = [torch.empty_like(padded) for _ in range(ctx.world)]  # equal sizes: short trailing blocks are padded
+        if padded.is_complex():
+            ctx.dist.all_gather([torch.view_as_real(p) for p in parts], torch.view_as_real(padded), group=ctx.group)
+        else:
+            ctx.dist.all_gather(parts, padded, group=ctx.group)
+        parts = [parts[r][: self.offsets[r + 1] - self.offsets[r]] for r in range(ctx.world)]
+        return torch.cat(parts, dim=0)
+
+
+# ------------------------------------------------------------------------------------------------
+# one rank's share of a sharded four-index transform
+# ------------------------------------------------------------------------------------------------
+class _RankTransform:
+    def __init__(self, ctx, rank, n, m, u_dtype, c_dtype):
+        self.ctx, self.rank, self.n, self.m = ctx, rank, n, m
+        self.engine = ctx.engine
+        self.u_dtype, self.c_dtype = u_dtype, c_dtype
+        self.t_dtype = torch.complex128 if torch.complex128 in (u_dtype, c_dtype) else torch.float64
+        self.a_block, self.a_off = block_partition(n, ctx.world)  # partition of the old leading index
+        self.r_block, self.r_off = block_partition(m, ctx.world)  # partition of the new indices r and p
+        self.Pu = padded_pitch(n, u_dtype)
+        self.P = padded_pitch(n, self.t_dtype)
+        self.A = self.a_off[rank + 1] - self.a_off[rank]
+        self.R = self.r_off[rank + 1] - self.r_off[rank]
+
+    # sizes (elements of t_dtype unless noted)
+    def recv_numel(self, rank):
+        return (self.r_off[rank + 1] - self.r_off[rank]) * self.m * self.n * self.P
+
+    def out_numel(self, rank):
+        return (self.r_off[rank + 1] - self.r_off[rank]) * self.m**3
+
+    def scratch_numel(self):
+        return max(self.m * self.A * self.n * self.P, self.m * self.R * self.m * self.P, 1)
+
+    def prepare(self, C, C_tilde):
+        eng, n, m = self.engine, self.n, self.m
+        self.img1 = eng.image(C, n, m, self.u_dtype, m, 1)
+        self.img2 = eng.image(C, n, m, self.t_dtype, m, 1)
+        if C_tilde is not None:
+            self.img3 = eng.image(C_tilde, n, m, self.t_dtype, 1, n)
+        else:
+            self.img3 = eng.image(C, n, m, self.t_dtype, m, 1, conj=True)  # C~ = C^dagger, basis_set.py:338-339
+        self.scratch = eng.empty(self.scratch_numel(), self.t_dtype)
+
+    def step1(self, u_in):
+        """T1[s, a_loc, b, c] = sum_d u[a_loc, b, c, d] C[d, s]  (new index slowest, c at pitch P)."""
+        eng, n, m, A, P = self.engine, self.n, self.m, self.A, self.P
+        if A == 0:
+            return
+        src = u_in
+        if self.Pu != n:
+            padded = eng.empty(A * n * n * self.Pu, self.u_dtype)
+            eng.pad_rows(u_in, A * n * n, n, self.Pu, padded)
+            src = padded
+        eng.quarter(src, A * n * n, n, self.Pu, self.img1, self.c_dtype, m, self.scratch, 0, n, 1, P, 1, 0, A * n * P)
+
+    def step2_scatter(self, recv):
+        """T2[r, s, a, b] = sum_c T1[s, a_loc, b, c] C[c, r], stored into the rank that owns r at
+        [r_loc][s][a][b] (b at pitch P): the a -> r re-partition rides on the epilogue."""
+        eng, n, m, A, P = self.engine, self.n, self.m, self.A, self.P
+        a0 = self.a_off[self.rank]
+        dests = [(recv[j], a0 * P) for j in range(self.ctx.world)]
+        eng.quarter_scatter(self.scratch, m * A * n, n, P, self.img2, self.c_dtype, m, dests, n, A, 1, P, n * P,
+                            self.r_block, m * n * P)
+
+    def step2_local(self, send):
+        """Collective schedule: T2[r, s, a_loc, b] written locally, blocks of r contiguous per destination."""
+        eng, n, m, A, P = self.engine, self.n, self.m, self.A, self.P
+        eng.quarter(self.scratch, m * A * n, n, P, self.img2, self.c_dtype, m, send, 0, n, 1, P, 1, 0, m * A * P)
+
+    def step3(self, recv_local):
+        """T3[q, r_loc, s, a] = sum_b T2[r_loc, s, a, b] C~[q, b]."""
+        eng, n, m, R, P = self.engine, self.n, self.m, self.R, self.P
+        eng.quarter(recv_local, R * m * n, n, P, self.img3, self.c_dtype, m, self.scratch, 0, n, 1, P, 1, 0, R * m * P)
+
+    def step3_blocked(self, recv_blocks):
+        """Collective schedule: the received buffer is [src][r_loc][s][a_loc(src)][b]; one launch per source
+        drops its planes between the others' (a at pitch P in T3)."""
+        eng, n, m, R, P = self.engine, self.n, self.m, self.R, self.P
+        offset = 0
+        for src in range(self.ctx.world):
+            A_src = self.a_off[src + 1] - self.a_off[src]
+            if A_src == 0 or R == 0:
+                continue
+            block = _slice(recv_blocks, offset, R * m * A_src * P)
+            eng.quarter(block, R * m * A_src, n, P, self.img3, self.c_dtype, m, self.scratch, self.a_off[src], A_src,
+                        1, P, 1, 0, R * m * P)
+            offset += R * m * A_src * P
+
+    def step4_scatter(self, out):
+        """u'[p, q, r, s] = sum_a T3[q, r_loc, s, a] C~[p, a], stored into the rank that owns p at
+        [p_loc][q][r][s]: the result is sharded on its leading index again."""
+        eng, n, m, R, P = self.engine, self.n, self.m, self.R, self.P
+        r0 = self.r_off[self.rank]
+        dests = [(out[j], r0 * m) for j in range(self.ctx.world)]
+        eng.quarter_scatter(self.scratch, m * R * m, n, P, self.img3, self.c_dtype, m, dests, m, R, 1, m, m * m,
+                            self.r_block, m**3)
+
+    def step4_local(self, out_local):
+        """Collective schedule: u'[p, q, r_loc, s] dense on this rank (sharded on the third index)."""
+        eng, n, m, R, P = self.engine, self.n, self.m, self.R, self.P
+        eng.quarter(self.scratch, m * R * m, n, P, self.img3, self.c_dtype, m, out_local, 0, m * R * m, 1, 0, 1, 0,
+                    m * R * m)
+
+
+def _slice(buf, offset, numel):
+    if isinstance(buf, DeviceBuffer):
+        return DeviceBuffer(buf.at(offset), numel, buf.dtype)
+    return buf.slice(offset, numel)
+
+
+def transform_two_body_sharded(u, C, C_tilde=None):
+    """Four-index transform of a ``ShardedTwoBody``; returns a new handle sharded on the leading index.
+
+    Same contraction order (s, r, q, p) and operands as the single-GPU ``ops.transform_two_body``
+    (reference basis_set.py:336-350).  Rectangular ``C`` (n, m) changes the extent; ``C_tilde`` (m, n)
+    defaults to ``C^dagger``.
+    """
+    ctx = u.ctx
+    n, m = C.shape
+    if n != u.n:
+        raise ValueError(f"C has {n} rows but u has {u.n} orbitals")
+    work = {r: _RankTransform(ctx, r, n, m, u.dtype, C.dtype) for r in ctx.local_ranks}
+    t_dtype = next(iter(work.values())).t_dtype
+    for w in work.values():
+        w.prepare(C, C_tilde)
+    any_w = next(iter(work.values()))
+
+    if ctx.exchange == "peer":
+        recv = ctx.shared_cached("recv", [any_w.recv_numel(r) for r in range(ctx.world)], t_dtype)
+        out_numels = [any_w.out_numel(r) for r in range(ctx.world)]
+        if u.spare is not None and u.dtype == t_dtype and m == n:
+            out = u.spare  # ping-pong: reuse the buffers of the tensor replaced one call earlier
+        else:
+            out = ctx.shared_empty(out_numels, t_dtype)
+        ctx.barrier()  # every rank is done with whatever it last read from these buffers
+        for r, w in work.items():
+            w.step1(u.buffers[r][r])
+            w.step2_scatter(recv[r])
+        ctx.barrier()  # all tiles of T2 have landed
+        for r, w in work.items():
+            w.step3(recv[r][r])
+            w.step4_scatter(out[r])
+        ctx.barrier()  # all tiles of u' have landed
+        spare = u.buffers if (u.dtype == t_dtype and m == n) else None
+        return ShardedTwoBody(ctx, m, t_dtype, out, spare)
+
+    # collective schedule (one rank per process)
+    (r, w), = work.items()
+    eng, P = ctx.engine, w.P
+    send = eng.empty(m * m * w.A * P, t_dtype)
+    recv = eng.empty(w.R * m * n * P, t_dtype)
+    w.step1(u.buffers[r][r])
+    w.step2_local(send)
+    send_splits = [(w.r_off[j + 1] - w.r_off[j]) * m * w.A * P for j in range(ctx.world)]
+    recv_splits = [w.R * m * (w.a_off[k + 1] - w.a_off[k]) * P for k in range(ctx.world)]
+    ctx.all_to_all(send, send_splits, recv, recv_splits)
+    w.step3_blocked(recv)
+    out_local = eng.empty(m * w.R * m * m, t_dtype)  # u'[p, q, r_loc, s]
+    w.step4_local(out_local)
+    # r -> p re-partition: send [p in P_j][q][r_loc][s], receive [p_loc][q][r_loc(k)][s] from every k
+    send_splits = [(w.r_off[j + 1] - w.r_off[j]) * m * w.R * m for j in range(ctx.world)]
+    recv_splits = [w.R * m * (w.r_off[k + 1] - w.r_off[k]) * m for k in range(ctx.world)]
+    staged = eng.empty(sum(recv_splits), t_dtype)
+    ctx.all_to_all(out_local, send_splits, staged, recv_splits)
+    result = ShardedTwoBody(ctx, m, t_dtype, {r: {r: eng.empty(w.R * m**3, t_dtype)}})
+    dense = result.local(r)
+    offset = 0
+    for k in range(ctx.world):
+        Rk = w.r_off[k + 1] - w.r_off[k]
+        block = staged.as_tensor()[offset : offset + recv_splits[k]].view(w.R, m, Rk, m)
+        dense[:, :, w.r_off[k] : w.r_off[k + 1], :] = block  # data movement only
+        offset += recv_splits[k]
+    return result
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference-facing container, sharded
+# ------------------------------------------------------------------------------------------------
+class ShardedBasisSet:
+    """``h``, ``s`` replicated on every rank, ``u`` a ``ShardedTwoBody``.
+
+    Mirrors the part of ``BasisSet`` that the hot path needs at multi-GPU scale: ``change_basis``
+    (reference basis_set.py:413-464), spin doubling fused with anti-symmetrisation
+    (:530-636, :772-778) and the general Fock matrix (general_orbital_system.py:119-159).
+    """
+
+    def __init__(self, ctx, l, h, s, u, includes_spin=False, anti_symmetrized_u=False):
+        self.ctx = ctx
+        self.l = l
+        self.h = h
+        self.s = s
+        self.u = u
+        self.includes_spin = includes_spin
+        self.anti_symmetrized_u = anti_symmetrized_u
+
+    @classmethod
+    def from_slabs(cls, ctx, n, h, s, slab_fn, dtype=torch.float64, **flags):
+        """``slab_fn(p0, p1)`` returns this rank's ``(p1 - p0, n, n, n)`` planes (host or device array)."""
+        eng = ctx.engine
+        u = ShardedTwoBody.empty(ctx, n, dtype)
+        for r in ctx.local_ranks:
+            p0, p1 = u.planes(r)
+            if p1 > p0:
+                u.local(r).copy_(eng.asarray(slab_fn(p0, p1), dtype), non_blocking=True)
+        ctx.barrier()
+        return cls(ctx, n, eng.asarray(h), eng.asarray(s) if s is not None else None, u, **flags)
+
+    @classmethod
+    def from_global(cls, ctx, h, s, u, **flags):
+        """Every rank holds the same full array ``u`` (small n) and keeps its own planes."""
+        n = u.shape[0]
+        dtype = torch.complex128 if (u.is_complex() if isinstance(u, torch.Tensor) else u.dtype.kind == "c") else torch.float64
+        return cls.from_slabs(ctx, n, h, s, lambda p0, p1: u[p0:p1], dtype=dtype, **flags)
+
+    @classmethod
+    def from_spatial(cls, ctx, h, s, u_spatial, anti_symmetrize=True, out_dtype=torch.complex128):
+        """Spin-double a replicated spatial basis into a sharded spin-orbital one: every rank writes its
+        own planes P = 2p + sigma of the (2l)^4 tensor with the fused add_spin + anti-symmetrise (+ cast)
+        kernel -- no communication."""
+        from . import _arrays, ops
+
+        u_dev = _arrays.to_device(u_spatial)
+        l = u_dev.shape[0]
+        n = 2 * l
+        if u_dev.is_complex():
+            out_dtype = torch.complex128
+        u = ShardedTwoBody.empty(ctx, n, out_dtype)
+        for r in ctx.local_ranks:
+            p0, p1 = u.planes(r)
+            if p1 > p0:
+                ops.add_spin_two_body(u_dev, anti_symmetrize=anti_symmetrize, out_dtype=out_dtype, planes=(p0, p1),
+                                      out=u.local(r))
+        ctx.barrier()
+        h2 = ops.add_spin_one_body(_arrays.to_device(h), out_dtype=out_dtype)
+        s2 = ops.add_spin_one_body(_arrays.to_device(s), out_dtype=out_dtype)
+        return cls(ctx, n, h2, s2, u, includes_spin=True, anti_symmetrized_u=bool(anti_symmetrize))
+
+    def change_basis(self, C, C_tilde=None):
+        """``h, s <- C~ X C`` on every rank (replicated, O(n^3)); ``u`` through the sharded transform."""
+        from . import _arrays, ops
+
+        C = _arrays.to_device(C)
+        C_tilde = _arrays.to_device(C_tilde) if C_tilde is not None else None
+        if C_tilde is not None:
+            dt = torch.complex128 if torch.complex128 in (C.dtype, C_tilde.dtype) else torch.float64
+            C, C_tilde = C.to(dt), C_tilde.to(dt)
+        self.l = C.shape[1]
+        self.h = ops.transform_one_body(self.h, C, C_tilde)
+        if self.s is not None:
+            self.s = ops.transform_one_body(self.s, C, C_tilde)
+        self.u = transform_two_body_sharded(self.u, C, C_tilde)
+
+    def construct_fock_matrix(self, h, u, n_occ, f=None):
+        """``f = h + sum_i u[p,i,q,i]``: every rank reduces the rows p it owns, then the rows are
+        all-gathered (n^2 elements)."""
+        from . import ops
+
+        ctx = self.ctx
+        n = u.n
+        if f is None:
+            f = torch.empty_like(h)
+        for r in ctx.local_ranks:
+            p0, p1 = u.planes(r)
+            if p1 > p0:
+                _native.call(
+                    "qs_fock_general", ops._ptr(h), ops._code(h), ctypes.c_void_p(u.buffers[r][r].at(0)),
+                    _CODES[u.dtype], n, int(n_occ), ops._ptr(f), p0, p1, ops._stream(),
+                )
+        if isinstance(ctx, ProcessContext) and ctx.world > 1:
+            block, offsets = u.block, u.offsets
+            padded = torch.zeros((ctx.world, block, n), dtype=f.dtype, device=f.device)
+            p0, p1 = u.planes(ctx.rank)
+            padded[ctx.rank, : p1 - p0] = f[p0:p1]
+            flat = torch.view_as_real(padded) if padded.is_complex() else padded
+            ctx.dist.all_reduce(flat, group=ctx.group)  # disjoint rows: sum == gather
+            for r in range(ctx.world):
+                q0, q1 = offsets[r], offsets[r + 1]
+                f[q0:q1] = padded[r, : q1 - q0]
+        return f

@@ -1,0 +1,76 @@
+"""TEST INFRASTRUCTURE: a numpy stand-in for ``quantum_systems_b200.sharded.CudaEngine``.
+
+It implements the documented semantics of ``qs_quarter_transform`` / ``qs_quarter_transform_scatter``
+(include/qsb200.h) on host buffers so that the sharded SCHEDULE (partition, strides, exchange
+layouts) can be exercised under gloo on a CPU-only box.  The product package never imports it.
+"""
+
+import numpy as np
+import torch
+
+
+class HostBuffer:
+    def __init__(self, tensor):
+        self.tensor = tensor
+        self.dtype = tensor.dtype
+        self.numel = tensor.numel()
+
+    def as_tensor(self):
+        return self.tensor
+
+    def slice(self, offset, numel):
+        return HostBuffer(self.tensor[offset : offset + numel])
+
+    def flat(self):
+        return self.tensor.numpy()
+
+
+class NumpyEngine:
+    def empty(self, numel, dtype):
+        return HostBuffer(torch.full((max(int(numel), 1),), float("nan"), dtype=dtype))
+
+    def asarray(self, a, dtype=None):
+        t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+        return t if dtype is None else t.to(dtype)
+
+    def image(self, M, K, W, a_dtype, stride_k, stride_w, conj=False):
+        flat = (M.numpy() if isinstance(M, torch.Tensor) else np.asarray(M)).reshape(-1)
+        k = np.arange(K)[:, None] * stride_k
+        w = np.arange(W)[None, :] * stride_w
+        dense = flat[k + w]
+        return dense.conj() if conj else dense
+
+    def pad_rows(self, src, rows, n, pitch, dst):
+        out = dst.flat()[: rows * pitch].reshape(rows, pitch)
+        out[:, :n] = src.flat()[: rows * n].reshape(rows, n)
+        out[:, n:] = 0
+
+    @staticmethod
+    def _product(A, X, K, lda, image):
+        rows = A.flat()[: X * lda].reshape(X, lda)[:, :K]
+        return rows @ image
+
+    def quarter(self, A, X, K, lda, image, m_dtype, W, out, out_offset, x_inner, sx0, sx1, w_inner, sw0, sw1):
+        if X <= 0:
+            return
+        res = self._product(A, X, K, lda, image)
+        x = np.arange(X)
+        w = np.arange(W)
+        ax = (x // x_inner) * sx1 + (x % x_inner) * sx0
+        aw = (w // w_inner) * sw1 + (w % w_inner) * sw0
+        out.flat()[out_offset + ax[:, None] + aw[None, :]] = res
+
+    def quarter_scatter(self, A, X, K, lda, image, m_dtype, W, dests, x_inner, x_mid, sx0, sx1, sx2, w_inner, sw0):
+        if X <= 0:
+            return
+        res = self._product(A, X, K, lda, image)
+        x = np.arange(X)
+        x_mid = max(x_mid, 1)
+        xq = x // x_inner
+        ax = (xq // x_mid) * sx2 + (xq % x_mid) * sx1 + (x % x_inner) * sx0
+        for j, (buf, off) in enumerate(dests):
+            cols = np.arange(j * w_inner, min((j + 1) * w_inner, W))
+            if len(cols) == 0:
+                continue
+            aw = (cols % w_inner) * sw0
+            buf.flat()[off + ax[:, None] + aw[None, :]] = res[:, cols]

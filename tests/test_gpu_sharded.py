@@ -1,0 +1,109 @@
+"""GPU parity of the sharded schedule.  On one GPU all W ranks are driven by one process
+(``EmulatedContext``): the scattering quarter GEMM writes into W destination buffers exactly as it
+writes into W peers' IPC mappings.  With >= 2 GPUs the real one-process-per-GPU path (CUDA IPC peer
+stores over NVLink, NCCL barriers) is run under torchrun by tests/_multi_gpu_worker.py."""
+
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import assert_close_scaled
+from oracle import qs_oracle as oracle
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def rand(rng, shape, complex_):
+    x = rng.standard_normal(shape)
+    return x + 1j * rng.standard_normal(shape) if complex_ else x
+
+
+def dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+@pytest.mark.parametrize("n,m,u_complex,c_complex,biorth", [
+    (16, 16, False, False, False),
+    (9, 9, False, False, False),
+    (13, 20, False, False, False),
+    (20, 12, True, True, True),
+    (12, 12, False, True, False),
+    (40, 40, False, False, False),
+])
+def test_emulated_sharded_transform(world, n, m, u_complex, c_complex, biorth):
+    from quantum_systems_b200 import sharded
+
+    rng = np.random.default_rng(100 * n + m + world)
+    u = rand(rng, (n,) * 4, u_complex)
+    C = rand(rng, (n, m), c_complex)
+    Ct = rand(rng, (m, n), c_complex) if biorth else None
+    ctx = sharded.EmulatedContext(world)
+    basis = sharded.ShardedBasisSet.from_global(ctx, np.eye(n), np.eye(n), u)
+    out = sharded.transform_two_body_sharded(basis.u, dev(C), None if Ct is None else dev(Ct))
+    expected = oracle.transform_two_body_elements(u, C, Ct)
+    got = out.gather().cpu().numpy()
+    assert got.dtype == expected.dtype
+    assert_close_scaled(got, expected, rel=1e-12)
+    if m == n and out.dtype == basis.u.dtype:
+        out2 = sharded.transform_two_body_sharded(out, dev(C), None if Ct is None else dev(Ct))
+        assert_close_scaled(out2.gather().cpu().numpy(), oracle.transform_two_body_elements(expected, C, Ct), rel=1e-11)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("out_complex", [False, True])
+def test_sharded_spin_doubling_change_basis_fock(world, out_complex):
+    """add_spin + anti_symmetrize on plane ranges, sharded change_basis, row-sharded Fock matrix."""
+    from quantum_systems_b200 import sharded
+
+    rng = np.random.default_rng(world)
+    l, n_occ = 7, 4
+    u = rng.standard_normal((l,) * 4)
+    h = rng.standard_normal((l, l))
+    s = np.eye(l)
+    ctx = sharded.EmulatedContext(world)
+    basis = sharded.ShardedBasisSet.from_spatial(
+        ctx, h, s, u, anti_symmetrize=True, out_dtype=torch.complex128 if out_complex else torch.float64
+    )
+    ref_u = oracle.anti_symmetrize_u(oracle.add_spin_two_body(u))
+    np.testing.assert_array_equal(basis.u.gather().cpu().numpy(), ref_u.astype(np.complex128 if out_complex else np.float64))
+    ref_h = oracle.add_spin_one_body(h)
+    C = np.linalg.qr(rng.standard_normal((2 * l, 2 * l)))[0]
+    basis.change_basis(dev(C))
+    ref_u2 = oracle.transform_two_body_elements(ref_u, C)
+    ref_h2 = oracle.transform_one_body_elements(ref_h, C)
+    assert_close_scaled(basis.u.gather().cpu().numpy(), ref_u2, rel=1e-12)
+    assert_close_scaled(basis.h.cpu().numpy(), ref_h2, rel=1e-12)
+    f = basis.construct_fock_matrix(basis.h, basis.u, n_occ)
+    assert_close_scaled(f.cpu().numpy(), oracle.construct_fock_matrix_general(ref_h2, ref_u2, n_occ), rel=1e-12)
+
+
+def test_scatter_rejects_too_many_destinations():
+    from quantum_systems_b200 import sharded
+
+    with pytest.raises(RuntimeError, match="at most"):
+        ctx = sharded.EmulatedContext(17)
+        basis = sharded.ShardedBasisSet.from_global(ctx, np.eye(34), np.eye(34), np.zeros((34,) * 4))
+        sharded.transform_two_body_sharded(basis.u, dev(np.eye(34)))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("exchange", ["peer", "collective"])
+def test_two_gpu_processes(exchange):
+    """One process per GPU under torchrun: CUDA IPC peer stores (or NCCL all_to_all) + NCCL barriers."""
+    world = min(torch.cuda.device_count(), 8)
+    world = 1 << (world.bit_length() - 1)
+    cmd = [
+        sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+        "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tests", "_multi_gpu_worker.py"),
+        exchange,
+    ]
+    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
+    assert "MULTI_GPU_OK" in proc.stdout

@@ -1,0 +1,111 @@
+"""Host-side logic of the sharded schedule on a CPU-only box: block partition, stride plans and both
+exchange layouts, checked against the numpy oracle.  The arithmetic of the quarter steps is supplied
+by tests/_numpy_engine.py (test infrastructure); the schedule under test is the product's
+``quantum_systems_b200.sharded``.  The multi-process test runs world_size 2 under gloo."""
+
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import qs_oracle as oracle
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from _numpy_engine import NumpyEngine  # noqa: E402
+
+
+def rand(rng, shape, complex_):
+    x = rng.standard_normal(shape)
+    return x + 1j * rng.standard_normal(shape) if complex_ else x
+
+
+def test_block_partition():
+    from quantum_systems_b200.sharded import block_partition
+
+    assert block_partition(400, 8) == (50, [0, 50, 100, 150, 200, 250, 300, 350, 400])
+    assert block_partition(10, 4) == (3, [0, 3, 6, 9, 10])
+    assert block_partition(3, 4) == (1, [0, 1, 2, 3, 3])  # trailing rank empty
+    for n in range(1, 40):
+        for w in range(1, 9):
+            block, off = block_partition(n, w)
+            assert off[0] == 0 and off[-1] == n and all(0 <= b - a <= block for a, b in zip(off, off[1:]))
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4])
+@pytest.mark.parametrize("n,m,u_complex,c_complex,biorth", [
+    (8, 8, False, False, False),
+    (9, 9, False, False, False),   # odd real extent: padded pitch
+    (7, 10, False, False, False),  # rectangular, grows
+    (10, 6, True, True, True),     # rectangular, shrinks, bi-orthogonal complex
+    (6, 6, False, True, False),    # real u, complex C
+])
+def test_emulated_peer_schedule_matches_oracle(world, n, m, u_complex, c_complex, biorth):
+    from quantum_systems_b200 import sharded
+
+    rng = np.random.default_rng(100 * n + m + world)
+    u = rand(rng, (n,) * 4, u_complex)
+    C = rand(rng, (n, m), c_complex)
+    Ct = rand(rng, (m, n), c_complex) if biorth else None
+    ctx = sharded.EmulatedContext(world, engine=NumpyEngine())
+    basis = sharded.ShardedBasisSet.from_global(ctx, np.eye(n), np.eye(n), u)
+    out = sharded.transform_two_body_sharded(basis.u, torch.from_numpy(C), None if Ct is None else torch.from_numpy(Ct))
+    expected = oracle.transform_two_body_elements(u, C, Ct)
+    got = out.gather().numpy()
+    assert got.shape == expected.shape and got.dtype == expected.dtype
+    np.testing.assert_allclose(got, expected, rtol=1e-12, atol=1e-12 * np.abs(expected).max())
+    # result is sharded on the leading index again, with the same block rule
+    assert [out.planes(r) for r in range(world)] == list(zip(out.offsets[:-1], out.offsets[1:]))
+    if m == n and not (u_complex != (c_complex or u_complex)):
+        # second transform recycles the first tensor's buffers (ping-pong) and must still be right
+        out2 = sharded.transform_two_body_sharded(out, torch.from_numpy(C), None if Ct is None else torch.from_numpy(Ct))
+        expected2 = oracle.transform_two_body_elements(expected, C, Ct)
+        np.testing.assert_allclose(out2.gather().numpy(), expected2, rtol=1e-11, atol=1e-11 * np.abs(expected2).max())
+
+
+def _free_port():
+    with socket.socket() as sock:
+        sock.bind(("127.0.0.1", 0))
+        return sock.getsockname()[1]
+
+
+def _gloo_worker(rank, world, port, n, m, complex_, results):
+    import torch.distributed as dist
+
+    from quantum_systems_b200 import sharded
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(7)
+        u = rand(rng, (n,) * 4, complex_)
+        C = rand(rng, (n, m), complex_)
+        ctx = sharded.ProcessContext(engine=NumpyEngine())
+        assert ctx.exchange == "collective"
+        basis = sharded.ShardedBasisSet.from_global(ctx, np.eye(n), np.eye(n), u)
+        p0, p1 = basis.u.planes(rank)
+        np.testing.assert_array_equal(basis.u.local().numpy(), u[p0:p1])
+        out = sharded.transform_two_body_sharded(basis.u, torch.from_numpy(C))
+        expected = oracle.transform_two_body_elements(u, C)
+        q0, q1 = out.planes(rank)
+        np.testing.assert_allclose(out.local().numpy(), expected[q0:q1], rtol=1e-12, atol=1e-12 * np.abs(expected).max())
+        full = out.gather().numpy()
+        np.testing.assert_allclose(full, expected, rtol=1e-12, atol=1e-12 * np.abs(expected).max())
+        results[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,m,complex_", [(8, 8, False), (7, 9, True)])
+def test_collective_schedule_world2_gloo(n, m, complex_):
+    import torch.multiprocessing as mp
+
+    world = 2
+    port = _free_port()
+    manager = mp.get_context("spawn").Manager()
+    results = manager.dict()
+    mp.spawn(_gloo_worker, args=(world, port, n, m, complex_, results), nprocs=world, join=True)
+    assert dict(results) == {0: "ok", 1: "ok"}
