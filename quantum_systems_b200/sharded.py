@@ -521,7 +521,7 @@ class ShardedBasisSet:
         return cls.from_slabs(ctx, n, h, s, lambda p0, p1: u[p0:p1], dtype=dtype, **flags)
 
     @classmethod
-    def from_spatial(cls, ctx, h, s, u_spatial, anti_symmetrize=True, out_dtype=torch.complex128):
+    def from_spatial(cls, ctx, h, s, u_spatial, anti_symmetrize=True, out_dtype=torch.complex128, into=None):
         """Spin-double a replicated spatial basis into a sharded spin-orbital one: every rank writes its
         own planes P = 2p + sigma of the (2l)^4 tensor with the fused add_spin + anti-symmetrise (+ cast)
         kernel -- no communication."""
@@ -532,7 +532,9 @@ class ShardedBasisSet:
         n = 2 * l
         if u_dev.is_complex():
             out_dtype = torch.complex128
-        u = ShardedTwoBody.empty(ctx, n, out_dtype)
+        u = into if into is not None else ShardedTwoBody.empty(ctx, n, out_dtype)
+        if u.n != n or u.dtype != out_dtype:
+            raise ValueError("`into` must be a ShardedTwoBody of extent 2 l and the requested dtype")
         for r in ctx.local_ranks:
             p0, p1 = u.planes(r)
             if p1 > p0:
