@@ -22,11 +22,22 @@
 
 namespace {
 
-constexpr int kBlockX = 128;    // rows of A per CTA
+#ifndef QS_L2_PROMOTION
+#define QS_L2_PROMOTION CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+#endif
+#ifndef QS_STAGES
+#define QS_STAGES 0             // 0 = as deep as shared memory allows (at most 8)
+#endif
+constexpr int kBlockX = 128;    // rows of A per CTA tile
 constexpr int kChunkK = 16;     // k' per pipeline stage (= one 128-byte swizzled row)
-constexpr int kStages = 4;
-constexpr int kConsumerWarps = 4;
-constexpr int kThreads = kConsumerWarps * 32;
+constexpr int kGroups = 2;      // MMA warp groups that ping-pong on the tensor pipe
+constexpr int kGroupWarps = 4;  // one warp per SM sub-partition
+constexpr int kMmaWarps = kGroups * kGroupWarps;
+constexpr int kThreads = (kMmaWarps + 4) * 32;  // + the producer warp group (register donor, one lane issues TMA)
+// Register split (setmaxnreg, whole warp groups): the kernel launches with 168 registers per thread
+// (65536 / 384); the producer group shrinks to 24 and each MMA group grows to 240 (2 x 128 x 240 + 128 x 24 = 384 x 168).
+constexpr int kRegsProducer = 24;
+constexpr int kRegsMma = 240;
 constexpr int kATileBytes = kBlockX * kChunkK * 8;  // 16 KiB
 
 constexpr int kMaxDest = 16;    // destination buffers of a scattering store (ranks of one NVSwitch domain)
@@ -45,175 +56,329 @@ struct QuarterParams {
     int nchunks;              // ceil(K'/16)
     int last_halves;          // 8-k' halves of the last chunk that hold data (1 or 2)
     int tiles_w;              // column tiles in this group, each 8*NT wide
-    long long stagger_clocks; // start delay of the second CTA wave (0 = none)
     // store address = (w/w_inner)*sw1 + (w%w_inner)*sw0 + x2*sx2 + x1*sx1 + x0*sx0 with
     // x = (x2 * x_mid + x1) * x_inner + x0, in OUTPUT ELEMENTS (w = w' for real output, w'/2 for complex)
     uint32_t x_inner, x_mid, w_inner;
     long long sx0, sx1, sx2, sw0, sw1;
+    int vec2;                 // real output: row pairs (x, x + 1), x even, are adjacent and 16-byte aligned
 };
 
-__device__ __forceinline__ int row_permutation(int g) {
-    // MMA row g of an 8-row group reads tile row perm(g): rows of lanes g, g+1 (same quarter-warp)
-    // differ in bit 2, which makes the swizzled LDS.128 conflict-free.
-    return (g >> 1) | ((g & 1) << 2);
-}
+#ifdef QS_DBG_NOWAIT
+#define QS_FULL_WAIT(bar, par) ((void)0)
+#else
+#define QS_FULL_WAIT(bar, par) mbar_wait(bar, par)
+#endif
 
+// Row ownership inside a warp's 32 x 8NT tile: MMA row g of m-tile mt is tile row
+//     row_base(g) + (mt & 1) + 16 * (mt >> 1),      row_base = {0, 4, 2, 6, 8, 12, 10, 14}[g].
+// (a) the two row groups of a quarter-warp (g = 2q, 2q + 1) differ in bit 2, so the TMA-swizzled LDS.128 fragment
+//     loads are conflict-free; (b) a thread owns PAIRS of adjacent rows (mt = 0,1 and mt = 2,3) and the 8 lanes of a
+//     column own 16 consecutive rows, so the epilogue writes whole 128-byte lines with 16-byte stores.
+__device__ __forceinline__ int row_base(int g) { return 2 * ((g >> 1) & 1) + 4 * (g & 1) + 8 * (g >> 2); }
+
+// One stage ring per MMA group: as many 16 KiB + NT KiB stages as fit, at most 6 (4 at NT = 8).
+template <int NT>
+struct RingConfig {
+    static constexpr int kBTileBytes = NT * 1024;  // 16 k' x 8*NT w' doubles
+    static constexpr int kStageBytes = kATileBytes + kBTileBytes;
+    static constexpr int kFit = (110 * 1024) / kStageBytes;
+    static constexpr int kStages = QS_STAGES > 0 ? QS_STAGES : (kFit < 6 ? kFit : 6);
+    static constexpr int kRingBytes = kStages * kStageBytes;
+    static constexpr int kSmemBytes = kGroups * kRingBytes + (kGroups * 2 * kStages + 2) * 8 + 1024;
+};
+
+// One persistent CTA per SM, 12 warps:
+//   warps 0-3     MMA group 0, one warp per SM sub-partition, a 32 x 8NT accumulator tile each in registers;
+//   warps 4-7     MMA group 1, same sub-partitions; the groups work on alternate tiles of the CTA;
+//   warps 8, 9    TMA producers, one per group, each running its own full/empty stage ring (one elected lane);
+//   warps 10, 11  idle; the producer warp group exists to donate its registers to the MMA groups (setmaxnreg).
+// Tile starts are ORDERED: a group may start tile i only after the other group has passed the midpoint of the
+// main loop of tile i - 1.  In steady state both groups are in their main loops half a tile apart (two warps per
+// sub-partition hide each other's fragment-load and barrier latencies), and each group's epilogue falls into the
+// middle of the other's main loop.  Without the ordering (two independent CTAs per SM) the epilogues drift into
+// phase -- the group that is behind runs at full speed while the one ahead stores -- and nothing hides them
+// (measured 81 % of the DMMA peak); with strict alternation (one group at a time) a lone warp per sub-partition
+// cannot hide its own LDS/scoreboard stalls (measured 86 %).
 template <int NT, bool COMPLEX_OUT>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 1)
 quarter_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ QuarterParams p) {
-    constexpr int kBTileBytes = NT * 1024;  // 16 k' x 8*NT w' doubles
-    constexpr int kStageBytes = kATileBytes + kBTileBytes;
+    using Ring = RingConfig<NT>;
+    constexpr int kBTileBytes = Ring::kBTileBytes;
+    constexpr int kStageBytes = Ring::kStageBytes;
+    constexpr int kStages = Ring::kStages;
 
     extern __shared__ unsigned char smem_raw[];
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bar_base = smem_base + kStages * kStageBytes;  // full[s] at +8s, empty[s] at +8(S+s)
+    uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    asm volatile("" : "+r"(smem_base));  // keep it in a register: ptxas otherwise re-derives it inside the main loop
+    // barriers behind the two rings: group g has full[s] at bar_base + 16 g S + 8 s, empty[s] S slots further
+    const uint32_t bar_base = smem_base + kGroups * Ring::kRingBytes;
+    const uint32_t bar_order = bar_base + kGroups * 2 * kStages * 8;  // order[g] at +8g
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t total_tiles = p.tiles_x * (uint32_t)p.tiles_w;
+    const uint32_t my_tiles = blockIdx.x < total_tiles ? (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) {
-            mbar_init(bar_base + 8 * s, 1);
-            mbar_init(bar_base + 8 * (kStages + s), kConsumerWarps);
+        for (int gs = 0; gs < kGroups * kStages; ++gs) {
+            const uint32_t base = bar_base + (gs / kStages) * 16 * kStages + (gs % kStages) * 8;
+            mbar_init(base, 1);
+            mbar_init(base + 8 * kStages, kGroupWarps);
         }
+        mbar_init(bar_order, kGroupWarps);
+        mbar_init(bar_order + 8, kGroupWarps);
         mbar_fence_init();
         prefetch_tensormap(&map_a);
     }
     __syncthreads();
 
-    // Persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The chunk ring runs straight
-    // across tile boundaries, so the loads of the next tile are in flight during this tile's epilogue.
-    // ===== TMA producer role (thread 0): the pj-th chunk of this CTA goes to stage pj % kStages =====
-    uint32_t pj = 0, ptile = blockIdx.x;
-    int pc = 0;
-    auto produce_next = [&]() {
-        if (ptile >= total_tiles) return;
-        const uint32_t s = pj % kStages;
-        const uint32_t full = bar_base + 8 * s;
-        if (pj >= kStages) mbar_wait(bar_base + 8 * (kStages + s), ((pj / kStages) - 1) & 1);
-        const uint32_t tw = ptile % (uint32_t)p.tiles_w;
-        const uint32_t px0 = (ptile / (uint32_t)p.tiles_w) * kBlockX;
-        mbar_expect_tx(full, kStageBytes);
-        const uint32_t dst = smem_base + s * kStageBytes;
-        tma_load_2d(dst, &map_a, pc * kChunkK, (int)px0, full);
-        bulk_load_1d(dst + kATileBytes, p.image + ((size_t)tw * p.nchunks + pc) * (kBTileBytes / 8), kBTileBytes, full);
-        ++pj;
-        if (++pc == p.nchunks) {
-            pc = 0;
-            ptile += gridDim.x;
+    if (warp >= kMmaWarps) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsProducer));
+        const int pg = warp - kMmaWarps;  // producer of group pg
+        if (pg >= kGroups) return;
+        // ===== TMA producer of group pg: chunk j of the group's tiles (in order) goes to stage j % kStages =====
+        if (lane == 0) {
+            const uint32_t ring = smem_base + pg * Ring::kRingBytes;
+            const uint32_t bar_full = bar_base + pg * 16 * kStages;
+            const uint32_t bar_empty = bar_full + 8 * kStages;
+            uint32_t j = 0;
+            for (uint32_t i = pg; i < my_tiles; i += kGroups) {
+                const uint32_t tile = blockIdx.x + i * gridDim.x;
+                const uint32_t tw = tile % (uint32_t)p.tiles_w;
+                const int px0 = (int)((tile / (uint32_t)p.tiles_w) * kBlockX);
+                const double* img = p.image + (size_t)tw * p.nchunks * (kBTileBytes / 8);
+                for (int c = 0; c < p.nchunks; ++c, ++j) {
+                    const uint32_t s = j % kStages;
+                    if (j >= (uint32_t)kStages) mbar_wait(bar_empty + 8 * s, ((j / kStages) - 1) & 1);
+                    const uint32_t full = bar_full + 8 * s;
+#ifdef QS_DBG_NOLOAD
+                    mbar_arrive(full);
+                    (void)px0; (void)img; (void)ring;
+#else
+                    mbar_expect_tx(full, kStageBytes);
+                    const uint32_t dst = ring + s * kStageBytes;
+                    tma_load_2d(dst, &map_a, c * kChunkK, px0, full);
+                    bulk_load_1d(dst + kATileBytes, img + (size_t)c * (kBTileBytes / 8), kBTileBytes, full);
+#endif
+                }
+            }
         }
-    };
-    if (threadIdx.x == 0) {
-        for (int c = 0; c < kStages - 1; ++c) produce_next();
+        return;
     }
 
-    // Co-resident CTAs (block b and b + #SMs share an SM) would otherwise run their epilogues at
-    // the same time and leave the tensor pipe idle; start the second wave half a tile late.
-    if (p.stagger_clocks > 0 && blockIdx.x >= (gridDim.x + 1) / 2) {
-        const long long t0 = clock64();
-        while (clock64() - t0 < p.stagger_clocks) __nanosleep(256);
-    }
-
-    // ===== MMA: warp w owns rows [32w, 32w+32) x all 8*NT columns of the CTA tile =====
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsMma));
+    // ===== MMA groups: warp wg of group `group` owns rows [32 wg, 32 wg + 32) x all 8*NT columns of its tile =====
+    const int group = warp >> 2;
+    const int wg = warp & 3;
+    const uint32_t ring = smem_base + group * Ring::kRingBytes;
+    const uint32_t bar_full = bar_base + group * 16 * kStages;
+    const uint32_t bar_empty = bar_full + 8 * kStages;
     const int g = lane >> 2;
     const int t = lane & 3;
-    const int prow = row_permutation(g);
+    const int rbase = row_base(g);
 
-    // A fragment address inside a stage: row r = 32*warp + 8*mt + prow (128 B per row), logical
-    // 16-byte chunk (4h + t) stored at chunk ^ (r & 7) by the TMA 128-byte swizzle; r & 7 == prow.
-    const uint32_t a_row_off = (uint32_t)(32 * warp + prow) * 128u;
-    const uint32_t a_chunk0 = (uint32_t)((t ^ prow) << 4);        // h = 0
-    const uint32_t a_chunk1 = (uint32_t)(((4 + t) ^ prow) << 4);  // h = 1
+    // A fragment address inside a stage: row r = 32*wg + rbase + (mt & 1) + 16*(mt >> 1) (128 B per row), logical
+    // 16-byte chunk (4h + t) stored at chunk ^ (r & 7) by the TMA 128-byte swizzle; r & 7 == (rbase & 7) | (mt & 1).
+    const uint32_t a_row_off = (uint32_t)(32 * wg + rbase) * 128u;
     const uint32_t b_lane_off = kATileBytes + (uint32_t)lane * 16u;
+    auto a_frag_off = [&](int mt, int h) {
+        return a_row_off + (uint32_t)((mt & 1) * 128 + (mt >> 1) * 2048) +
+               (uint32_t)(((4 * h + t) ^ ((rbase & 7) | (mt & 1))) << 4);
+    };
 
-    uint32_t j = 0;  // chunks consumed so far by this CTA
-    for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    // fragment loads and the two k-steps (4 k' each) of one half chunk.  Loop order nt-outer / mt-inner: b[nt] dies
+    // progressively during the second k-step and is re-loaded for the NEXT half right behind its last use, and
+    // the A fragments are double-buffered (a0 / a1), so one warp per sub-partition keeps the DMMA pipe fed
+    // across half and chunk boundaries (no second warp is there to fill a bubble during a group's turn).
+#ifdef QS_DBG_NOLDS
+    auto load_a = [&](double2(&a)[4], uint32_t stage, int h) {
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) a[mt] = make_double2(1.0 + lane + mt, 0.5 + h);
+    };
+    auto load_b = [&](uint32_t stage, int h, int nt) { return make_double2(2.0 + lane + nt, 0.25 + h); };
+#else
+    auto load_a = [&](double2(&a)[4], uint32_t stage, int h) {
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) a[mt] = lds_128(stage + a_frag_off(mt, h));
+    };
+    auto load_b = [&](uint32_t stage, int h, int nt) {
+        return lds_128(stage + b_lane_off + (uint32_t)(h * NT + nt) * 512u);
+    };
+#endif
+
+    for (uint32_t i = group; i < my_tiles; i += kGroups) {
+        const uint32_t tile = blockIdx.x + i * gridDim.x;
+
         double acc[4][NT][2];
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
 
-        for (int c = 0; c < p.nchunks; ++c, ++j) {
-            const uint32_t s = j % kStages;
-            if (threadIdx.x == 0) produce_next();
-            __syncwarp();
-            mbar_wait(bar_base + 8 * s, (j / kStages) & 1);
-            const uint32_t stage = smem_base + s * kStageBytes;
-            // the last chunk may hold <= 8 valid k': skip its all-zero second half
-            const int halves = (c == p.nchunks - 1) ? p.last_halves : 2;
+        // k-step on the .x halves of the fragments.  `tail_*`: the last B fragment of this half is still to be
+        // fetched (the reloads trail their last reader by one column group, so the LDS never waits for a DMMA
+        // that has not read its operands yet).
+        auto step_x = [&](const double2(&a)[4], double2(&b)[NT], bool tail, uint32_t tail_stage, int tail_h) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                if (h < halves) {
-                    double2 a[4];
-                    double2 b[NT];
+            for (int nt = 0; nt < NT; ++nt) {
 #pragma unroll
-                    for (int mt = 0; mt < 4; ++mt)
-                        a[mt] = lds_128(stage + a_row_off + mt * 1024u + (h ? a_chunk1 : a_chunk0));
-#pragma unroll
-                    for (int nt = 0; nt < NT; ++nt)
-                        b[nt] = lds_128(stage + b_lane_off + (uint32_t)(h * NT + nt) * 512u);
-#pragma unroll
-                    for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-                        for (int nt = 0; nt < NT; ++nt)
-                            dmma_8x8x4(acc[mt][nt][0], acc[mt][nt][1], a[mt].x, b[nt].x);
-#pragma unroll
-                    for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-                        for (int nt = 0; nt < NT; ++nt)
-                            dmma_8x8x4(acc[mt][nt][0], acc[mt][nt][1], a[mt].y, b[nt].y);
-                }
+                for (int mt = 0; mt < 4; ++mt) dmma_8x8x4(acc[mt][nt][0], acc[mt][nt][1], a[mt].x, b[nt].x);
+                if (nt == 0 && NT > 1 && tail) b[NT - 1] = load_b(tail_stage, tail_h, NT - 1);
             }
+        };
+        auto step_y = [&](const double2(&a)[4], const double2(&b)[NT]) {
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt) dmma_8x8x4(acc[mt][nt][0], acc[mt][nt][1], a[mt].y, b[nt].y);
+        };
+        // k-step on the .y halves; b[nt - 1] is re-loaded for the NEXT half behind column group nt
+        // (b[NT - 1] follows in the next step_x)
+        auto step_y_reload = [&](const double2(&a)[4], double2(&b)[NT], uint32_t next_stage, int next_h) {
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt) dmma_8x8x4(acc[mt][nt][0], acc[mt][nt][1], a[mt].y, b[nt].y);
+                if (NT == 1) b[0] = load_b(next_stage, next_h, 0);
+                else if (nt >= 1) b[nt - 1] = load_b(next_stage, next_h, nt - 1);
+            }
+        };
+
+        // chunk j of this group's ring: stage s, phase parity par
+        const uint32_t j = (i >> 1) * (uint32_t)p.nchunks;
+        uint32_t s = j % kStages, par = (j / kStages) & 1;
+        uint32_t stage = ring + s * kStageBytes;
+        double2 a0[4], a1[4], b[NT];
+        QS_FULL_WAIT(bar_full + 8 * s, par);
+        load_a(a0, stage, 0);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) b[nt] = load_b(stage, 0, nt);
+
+        // ordered start: the other group has passed the signal point (midpoint) of the main loop of tile i - 1
+        const uint32_t k = i >> 1;
+        if (i > 0) mbar_wait(bar_order + 8 * group, (group == 0 ? k - 1 : k) & 1);
+#ifdef QS_SIGNAL_END
+        const int signal_chunk = p.nchunks - 1;
+#elif defined(QS_SIGNAL_NUM)
+        const int signal_chunk = ((p.nchunks - 1) * QS_SIGNAL_NUM) >> 3;
+#else
+        const int signal_chunk = (p.nchunks - 1) >> 1;
+#endif
+
+        bool tail = false;  // b[NT - 1] of the half about to start is still to be fetched
+        for (int c = 0; c + 1 < p.nchunks; ++c) {
+            step_x(a0, b, tail, stage, 0);
+            load_a(a1, stage, 1);
+            step_y_reload(a0, b, stage, 1);
+            step_x(a1, b, true, stage, 1);
+            const uint32_t s_done = s;
+            if (++s == (uint32_t)kStages) {
+                s = 0;
+                par ^= 1;
+            }
+            const uint32_t next_stage = ring + s * kStageBytes;
+            QS_FULL_WAIT(bar_full + 8 * s, par);
+            load_a(a0, next_stage, 0);
+            step_y_reload(a1, b, next_stage, 0);
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_base + 8 * (kStages + s));
+            if (lane == 0) {
+                mbar_arrive(bar_empty + 8 * s_done);
+                if (c == signal_chunk) mbar_arrive(bar_order + 8 * (group ^ 1));
+            }
+            stage = next_stage;
+            tail = true;
+        }
+        // last chunk: it may hold <= 8 valid k', then its all-zero second half is skipped
+        step_x(a0, b, tail, stage, 0);
+        if (p.last_halves == 2) {
+            load_a(a1, stage, 1);
+            step_y_reload(a0, b, stage, 1);
+            step_x(a1, b, true, stage, 1);
+            step_y(a1, b);
+        } else {
+            step_y(a0, b);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(bar_empty + 8 * s);
+            if (signal_chunk == p.nchunks - 1) mbar_arrive(bar_order + 8 * (group ^ 1));
         }
 
-        // ===== epilogue: rotated / strided store straight from the accumulators =====
+        // ===== epilogue: rotated / strided / scattering store straight from the accumulators =====
+#ifdef QS_DBG_NOSTORE
+        {
+            double sum = 0.0;
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) sum += acc[mt][nt][0] + acc[mt][nt][1];
+            if (sum == 1.2345e-300) p.out[0] = sum;
+            continue;
+        }
+#endif
         const uint32_t tile_w = tile % (uint32_t)p.tiles_w;
         const uint32_t x0 = (tile / (uint32_t)p.tiles_w) * kBlockX;
         long long xoff[4];
         bool xok[4];
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt) {
-            const uint32_t x = x0 + 32 * warp + 8 * mt + prow;
+            const uint32_t x = x0 + 32 * wg + rbase + (mt & 1) + 16 * (mt >> 1);
             xok[mt] = x < p.X;
             const uint32_t xq = x / p.x_inner;
             const uint32_t xr = x - xq * p.x_inner;
-            const uint32_t x2 = xq / p.x_mid;
-            const uint32_t x1 = xq - x2 * p.x_mid;
-            xoff[mt] = (long long)x2 * p.sx2 + (long long)x1 * p.sx1 + (long long)xr * p.sx0;
+            long long off = (long long)xr * p.sx0;
+            if (p.x_mid != 0xFFFFFFFFu) {
+                const uint32_t x2 = xq / p.x_mid;
+                const uint32_t x1 = xq - x2 * p.x_mid;
+                off += (long long)x2 * p.sx2 + (long long)x1 * p.sx1;
+            } else {
+                off += (long long)xq * p.sx1;
+            }
+            xoff[mt] = off;
         }
         const uint32_t wbase = p.w_first + tile_w * (8 * NT);
+        const bool plain_w = p.w_inner == 1 && p.ndest == 0;  // plain rotated store: column address = w * sw1
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
             const uint32_t wp = wbase + 8 * nt + 2 * t;  // real column of acc[..][nt][0]; wp + 1 for [1]
             if (COMPLEX_OUT) {
                 if (wp < p.Wp) {
                     const uint32_t w = wp >> 1;
-                    const uint32_t wq = w / p.w_inner;
-                    const uint32_t wr = w - wq * p.w_inner;
-                    const long long woff = (long long)wq * p.sw1 + (long long)wr * p.sw0;
-                    double* const base = p.ndest ? p.outs[wq] : p.out;
+                    double* col;
+                    if (plain_w) {
+                        col = p.out + 2 * ((long long)w * p.sw1);
+                    } else {
+                        const uint32_t wq = w / p.w_inner;
+                        const uint32_t wr = w - wq * p.w_inner;
+                        col = (p.ndest ? p.outs[wq] : p.out) + 2 * ((long long)wq * p.sw1 + (long long)wr * p.sw0);
+                    }
 #pragma unroll
                     for (int mt = 0; mt < 4; ++mt)
                         if (xok[mt])
-                            *reinterpret_cast<double2*>(base + 2 * (woff + xoff[mt])) =
-                                make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+                            *reinterpret_cast<double2*>(col + 2 * xoff[mt]) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
                 }
             } else {
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const uint32_t w = wp + e;
                     if (w < p.Wp) {
-                        const uint32_t wq = w / p.w_inner;
-                        const uint32_t wr = w - wq * p.w_inner;
-                        const long long woff = (long long)wq * p.sw1 + (long long)wr * p.sw0;
-                        double* const base = p.ndest ? p.outs[wq] : p.out;
+                        double* col;
+                        if (plain_w) {
+                            col = p.out + (long long)w * p.sw1;
+                        } else {
+                            const uint32_t wq = w / p.w_inner;
+                            const uint32_t wr = w - wq * p.w_inner;
+                            col = (p.ndest ? p.outs[wq] : p.out) + (long long)wq * p.sw1 + (long long)wr * p.sw0;
+                        }
+                        if (p.vec2) {
+                            // rows (mt = 0, 1) and (mt = 2, 3) are adjacent and 16-byte aligned in the output
+                            if (xok[0]) *reinterpret_cast<double2*>(col + xoff[0]) = make_double2(acc[0][nt][e], acc[1][nt][e]);
+                            if (xok[2]) *reinterpret_cast<double2*>(col + xoff[2]) = make_double2(acc[2][nt][e], acc[3][nt][e]);
+                        } else {
 #pragma unroll
-                        for (int mt = 0; mt < 4; ++mt)
-                            if (xok[mt]) base[woff + xoff[mt]] = acc[mt][nt][e];
+                            for (int mt = 0; mt < 4; ++mt)
+                                if (xok[mt]) col[xoff[mt]] = acc[mt][nt][e];
+                        }
                     }
                 }
             }
@@ -338,25 +503,17 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-int g_stagger = 1;  // QS_STAGGER=0 disables the second-wave start delay (tuning aid)
-
 template <int NT, bool CO>
-int launch_variant(const CUtensorMap& map, QuarterParams p, cudaStream_t st) {
-    constexpr int smem = kStages * (kATileBytes + NT * 1024) + 2 * kStages * 8 + 1024;
+int launch_variant(const CUtensorMap& map, const QuarterParams& p, cudaStream_t st) {
+    constexpr int smem = RingConfig<NT>::kSmemBytes;
     static bool configured = false;
     if (!configured) {
         QS_CUDA(cudaFuncSetAttribute(quarter_gemm_kernel<NT, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        QS_CUDA(cudaFuncSetAttribute(quarter_gemm_kernel<NT, CO>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                     cudaSharedmemCarveoutMaxShared));
-        const char* env = getenv("QS_STAGGER");
-        if (env) g_stagger = atoi(env);
         configured = true;
     }
     const int64_t total = (int64_t)p.tiles_x * p.tiles_w;
-    const int64_t resident = 2LL * qs_sm_count();
+    const int64_t resident = qs_sm_count();  // one persistent CTA per SM
     const int64_t grid = total < resident ? total : resident;
-    // half a tile of tensor-pipe time when two CTAs share an SM: nchunks * (4 * NT * 4 DMMA) * 16 clk
-    p.stagger_clocks = (g_stagger && grid > resident / 2) ? (long long)p.nchunks * NT * 256 : 0;
     quarter_gemm_kernel<NT, CO><<<(unsigned)grid, kThreads, smem, st>>>(map, p);
     QS_LAUNCH_CHECK();
     return QS_OK;
@@ -474,13 +631,18 @@ int quarter_launch(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda
     const cuuint32_t box[2] = {kChunkK, kBlockX};
     const cuuint32_t estr[2] = {1, 1};
     CUresult cr = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void*>(A), gdim, gstride, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, QS_L2_PROMOTION,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) {
         qs_set_error("cuTensorMapEncodeTiled failed with CUresult %d (X=%lld K'=%d pitch=%lld)", (int)cr, (long long)X,
                      tl.Kp, (long long)pitch_bytes);
         return QS_ERR_CUDA;
     }
+
+    // 16-byte row-pair stores of the real epilogue need adjacent, aligned rows and even strides everywhere
+    int vec2 = !out_complex && sx0 == 1 && x_inner % 2 == 0 && X % 2 == 0 && sx1 % 2 == 0 && sx2 % 2 == 0 &&
+               sw0 % 2 == 0 && (n_dest > 0 || sw1 % 2 == 0) && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    for (int64_t d = 0; d < n_dest; ++d) vec2 = vec2 && (reinterpret_cast<uintptr_t>(out_table[d]) & 15) == 0;
 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int span = -1;
@@ -500,7 +662,6 @@ int quarter_launch(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda
         p.nchunks = tl.nchunks;
         p.last_halves = tl.last_halves;
         p.tiles_w = gr.tiles_w;
-        p.stagger_clocks = 0;
         p.x_inner = (uint32_t)x_inner;
         p.x_mid = (uint32_t)x_mid;
         p.w_inner = (uint32_t)w_inner;
@@ -509,6 +670,7 @@ int quarter_launch(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda
         p.sx2 = sx2;
         p.sw0 = sw0;
         p.sw1 = n_dest ? 0 : sw1;
+        p.vec2 = vec2;
         QS_REQUIRE((int64_t)p.tiles_x * p.tiles_w < (1LL << 31), "qs_quarter_transform: too many tiles");
         const int rc = out_complex ? launch_nt<true>(gr.NT, map, p, st) : launch_nt<false>(gr.NT, map, p, st);
         if (rc) return rc;
