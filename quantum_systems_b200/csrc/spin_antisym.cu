@@ -67,9 +67,46 @@ __global__ void __launch_bounds__(256) add_spin_kernel(const double* __restrict_
     }
     __syncthreads();
 
+    constexpr int OD = OUT_COMPLEX ? 2 : 1;
+    if (OUT_COMPLEX) {
+        // A spin row holds 64 complex numbers (1 KiB): lane tx writes columns tx and tx + 32 so that each store
+        // instruction of the warp covers 512 contiguous bytes (whole sectors, whole lines).
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2) {
+            const long long Q = 2LL * q + s2;
+            double* plane = out + (((long long)blockIdx.z * n + Q) * n) * n * OD;
+            for (int i = ty; i < kTile; i += 8) {
+                const int r = r0 + i;
+                if (r >= l) break;
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    double* row = plane + ((2LL * r + g) * n + 2LL * s0) * OD;
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        const int c = tx + 32 * half;  // spin column inside the tile: S = 2 s0 + c
+                        const int sl = c >> 1, d = c & 1;
+                        if (s0 + sl < l) {
+                            const bool direct = (s1 == g) && (s2 == d);
+                            const bool exch = ANTISYM && (s1 == d) && (s2 == g);
+                            double vr = 0.0, vi = 0.0;
+                            if (direct) {
+                                vr = dre[i][sl];
+                                if (IN_COMPLEX) vi = dim_[i][sl];
+                            }
+                            if (exch) {
+                                vr -= ere[sl][i];
+                                if (IN_COMPLEX) vi -= eim[sl][i];
+                            }
+                            reinterpret_cast<double2*>(row)[c] = make_double2(vr, vi);
+                        }
+                    }
+                }
+            }
+        }
+        return;
+    }
     const int s = s0 + tx;
     if (s >= l) return;
-    constexpr int OD = OUT_COMPLEX ? 2 : 1;
 #pragma unroll
     for (int s2 = 0; s2 < 2; ++s2) {
         const long long Q = 2LL * q + s2;
@@ -77,67 +114,86 @@ __global__ void __launch_bounds__(256) add_spin_kernel(const double* __restrict_
         for (int i = ty; i < kTile; i += 8) {
             const int r = r0 + i;
             if (r >= l) break;
-            const double ar = dre[i][tx], ai = IN_COMPLEX ? dim_[i][tx] : 0.0;
-            const double br = ANTISYM ? ere[tx][i] : 0.0, bi = (ANTISYM && IN_COMPLEX) ? eim[tx][i] : 0.0;
+            const double ar = dre[i][tx];
+            const double br = ANTISYM ? ere[tx][i] : 0.0;
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
                 // element d of the pair (S = 2s + d): direct if s1==g && s2==d, exchange if s1==d && s2==g
-                double vr[2], vi[2];
+                double vr[2];
 #pragma unroll
                 for (int d = 0; d < 2; ++d) {
                     const bool direct = (s1 == g) && (s2 == d);
                     const bool exch = ANTISYM && (s1 == d) && (s2 == g);
                     vr[d] = (direct ? ar : 0.0) - (exch ? br : 0.0);
-                    vi[d] = (direct ? ai : 0.0) - (exch ? bi : 0.0);
                 }
-                double* row = plane + ((2LL * r + g) * n + 2LL * s) * OD;
-                if (OUT_COMPLEX) {
-                    reinterpret_cast<double2*>(row)[0] = make_double2(vr[0], vi[0]);
-                    reinterpret_cast<double2*>(row)[1] = make_double2(vr[1], vi[1]);
-                } else {
-                    reinterpret_cast<double2*>(row)[0] = make_double2(vr[0], vr[1]);
-                }
+                double* row = plane + ((2LL * r + g) * n + 2LL * s);
+                reinterpret_cast<double2*>(row)[0] = make_double2(vr[0], vr[1]);
             }
         }
     }
 }
 
-// out[p,q,r,s] = u[p,q,r,s] - u[p,q,s,r]; grid: x = tile(r,s), y = q, z = p - p_begin; block (32, 8)
+// out[p,q,r,s] = u[p,q,r,s] - u[p,q,s,r].  One block owns the PAIR of 32x32 tiles (R,S) and (S,R), R <= S, of one
+// (p,q) plane: every element is read once (T1 = u[R,S], T2 = u[S,R]) and both results are written,
+// out[R,S] = T1 - T2^T and out[S,R] = T2 - T1^T -- the algorithmic minimum of one read and one write pass.
+// grid: x = tile pair, y = q, z = p - p_begin; block (32, 8)
 template <bool COMPLEX>
 __global__ void __launch_bounds__(256) antisym_kernel(const double* __restrict__ u, double* __restrict__ out, int n,
                                                        int tiles, long long p_begin) {
-    __shared__ double ere[kTile][kTile + 1];
-    __shared__ double eim[COMPLEX ? kTile : 1][kTile + 1];
-    const int tr = blockIdx.x / tiles, ts = blockIdx.x % tiles;
+    constexpr int ED = COMPLEX ? 2 : 1;
+    __shared__ double t1[ED][kTile][kTile + 1];
+    __shared__ double t2[ED][kTile][kTile + 1];
+    // linear pair index -> (tr <= ts): row tr starts at tr * tiles - tr (tr - 1) / 2
+    int tr = 0, rem = blockIdx.x;
+    while (rem >= tiles - tr) {
+        rem -= tiles - tr;
+        ++tr;
+    }
+    const int ts = tr + rem;
     const int r0 = tr * kTile, s0 = ts * kTile;
     const long long plane = (((long long)(p_begin + blockIdx.z) * n + blockIdx.y) * n) * n;
     const long long oplane = (((long long)blockIdx.z * n + blockIdx.y) * n) * n;
     const int tx = threadIdx.x, ty = threadIdx.y;
     for (int i = ty; i < kTile; i += 8) {
-        if (s0 + i < n && r0 + tx < n) {
+        if (r0 + i < n && s0 + tx < n) {
+            const long long idx = plane + (long long)(r0 + i) * n + s0 + tx;
+            if (COMPLEX) {
+                const double2 v = reinterpret_cast<const double2*>(u)[idx];
+                t1[0][i][tx] = v.x;
+                t1[ED - 1][i][tx] = v.y;
+            } else {
+                t1[0][i][tx] = u[idx];
+            }
+        }
+        if (tr != ts && s0 + i < n && r0 + tx < n) {
             const long long idx = plane + (long long)(s0 + i) * n + r0 + tx;
             if (COMPLEX) {
                 const double2 v = reinterpret_cast<const double2*>(u)[idx];
-                ere[i][tx] = v.x;
-                eim[i][tx] = v.y;
+                t2[0][i][tx] = v.x;
+                t2[ED - 1][i][tx] = v.y;
             } else {
-                ere[i][tx] = u[idx];
+                t2[0][i][tx] = u[idx];
             }
         }
     }
     __syncthreads();
-    const int s = s0 + tx;
-    if (s >= n) return;
+    double(*other)[kTile][kTile + 1] = (tr == ts) ? t1 : t2;  // a diagonal tile is its own partner
     for (int i = ty; i < kTile; i += 8) {
-        const int r = r0 + i;
-        if (r >= n) break;
-        const long long idx = plane + (long long)r * n + s;
-        const long long oidx = oplane + (long long)r * n + s;
-        if (COMPLEX) {
-            const double2 v = reinterpret_cast<const double2*>(u)[idx];
-            reinterpret_cast<double2*>(out)[oidx] = make_double2(v.x - ere[tx][i], v.y - eim[tx][i]);
-        } else {
-            out[oidx] = u[idx] - ere[tx][i];
+        if (r0 + i < n && s0 + tx < n) {
+            const long long oidx = oplane + (long long)(r0 + i) * n + s0 + tx;
+            if (COMPLEX)
+                reinterpret_cast<double2*>(out)[oidx] =
+                    make_double2(t1[0][i][tx] - other[0][tx][i], t1[ED - 1][i][tx] - other[ED - 1][tx][i]);
+            else
+                out[oidx] = t1[0][i][tx] - other[0][tx][i];
+        }
+        if (tr != ts && s0 + i < n && r0 + tx < n) {
+            const long long oidx = oplane + (long long)(s0 + i) * n + r0 + tx;
+            if (COMPLEX)
+                reinterpret_cast<double2*>(out)[oidx] =
+                    make_double2(t2[0][i][tx] - t1[0][tx][i], t2[ED - 1][i][tx] - t1[ED - 1][tx][i]);
+            else
+                out[oidx] = t2[0][i][tx] - t1[0][tx][i];
         }
     }
 }
@@ -257,7 +313,7 @@ extern "C" int qs_anti_symmetrize(const void* u, int dtype, int64_t n, void* out
     if (p_begin == p_end) return QS_OK;
     const int tiles = (int)qs_ceil_div(n, kTile);
     const dim3 block(32, 8);
-    const dim3 grid((unsigned)(tiles * tiles), (unsigned)n, (unsigned)(p_end - p_begin));
+    const dim3 grid((unsigned)(tiles * (tiles + 1) / 2), (unsigned)n, (unsigned)(p_end - p_begin));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int span = -1;
     qs_timing_begin(QS_FAMILY_SPIN_PASS, 2.0 * (double)(p_end - p_begin) * n * n * n * 8.0 * qs_elem_doubles(dtype),
