@@ -1,0 +1,114 @@
+"""Parity at BASELINE.json's full single-GPU sizes.
+
+Where the numpy oracle finishes in seconds it is run directly (config 3: the l = 100, G = 2001 grid build;
+config 2: the n = 128 four-index transform, ~6 s on 16 cores).  On top of that, size-independent properties of
+the transform are checked at n = 128: a closed-form result for separable input, the round trip through an
+orthonormal basis and back, linearity, and preservation of anti-symmetry.  torch is used here only as the
+CHECKER of the CUDA path (einsum on the device), never by the product."""
+
+import numpy as np
+import pytest
+
+from conftest import assert_close_scaled
+from oracle import qs_oracle as oracle
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+N = 128
+
+
+def rel_err(got, ref):
+    return float((got - ref).abs().max() / ref.abs().max())
+
+
+@pytest.fixture(scope="module")
+def orthonormal():
+    rng = np.random.default_rng(1)
+    return torch.from_numpy(np.linalg.qr(rng.standard_normal((N, N)))[0]).cuda()
+
+
+def test_config2_transform_matches_oracle():
+    """configs[1]: n = 128 real, orthonormal C -- the whole 2.1 GB result against the numpy oracle."""
+    from quantum_systems_b200 import ops
+
+    rng = np.random.default_rng(2)
+    u = rng.standard_normal((N,) * 4)
+    C = np.linalg.qr(rng.standard_normal((N, N)))[0]
+    expected = oracle.transform_two_body_elements(u, C)
+    got = ops.transform_two_body(torch.from_numpy(u).cuda(), torch.from_numpy(C).cuda()).cpu().numpy()
+    assert_close_scaled(got, expected, rel=1e-12)
+
+
+def test_separable_input_closed_form(orthonormal):
+    """u = sum_t A_t (x) B_t  =>  u' = sum_t (C~ A_t C) (x) (C~ B_t C), exactly."""
+    from quantum_systems_b200 import ops
+
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    A = torch.randn((4, N, N), dtype=torch.float64, device="cuda", generator=gen)
+    B = torch.randn((4, N, N), dtype=torch.float64, device="cuda", generator=gen)
+    u = torch.einsum("tpr,tqs->pqrs", A, B).contiguous()
+    C = orthonormal
+    got = ops.transform_two_body(u, C)
+    At = torch.stack([ops.transform_one_body(a.contiguous(), C) for a in A])
+    Bt = torch.stack([ops.transform_one_body(b.contiguous(), C) for b in B])
+    # the one-body transform is itself pinned to the oracle
+    assert_close_scaled(At[0].cpu().numpy(), oracle.transform_one_body_elements(A[0].cpu().numpy(), C.cpu().numpy()))
+    expected = torch.einsum("tpr,tqs->pqrs", At, Bt)
+    assert rel_err(got, expected) <= 1e-12
+
+
+def test_round_trip_and_linearity(orthonormal):
+    from quantum_systems_b200 import ops
+
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    u1 = torch.randn((N,) * 4, dtype=torch.float64, device="cuda", generator=gen)
+    C = orthonormal
+    Cinv = C.transpose(0, 1).contiguous()
+    t1 = ops.transform_two_body(u1, C)
+    back = ops.transform_two_body(t1, Cinv)
+    assert rel_err(back, u1) <= 1e-12
+    # explicit bra coefficients equal to the default C^dagger give the same result bit for bit
+    assert torch.equal(ops.transform_two_body(u1, C, Cinv), t1)
+    del back
+    u2 = torch.randn((N,) * 4, dtype=torch.float64, device="cuda", generator=gen)
+    t2 = ops.transform_two_body(u2, C)
+    combo = ops.transform_two_body(0.75 * u1 - 1.5 * u2, C)
+    assert rel_err(combo, 0.75 * t1 - 1.5 * t2) <= 1e-12
+
+
+def test_antisymmetry_is_preserved_through_spin_doubling_and_basis_change(orthonormal):
+    from quantum_systems_b200 import ops
+
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    l = N // 2
+    u = torch.randn((l,) * 4, dtype=torch.float64, device="cuda", generator=gen)
+    u = 0.5 * (u + u.permute(1, 0, 3, 2)).contiguous()
+    spin = ops.add_spin_two_body(u, anti_symmetrize=True)
+    # fused pass == the two separate passes, bit for bit
+    assert torch.equal(spin, ops.anti_symmetrize(ops.add_spin_two_body(u)))
+    assert torch.equal(spin, -spin.permute(0, 1, 3, 2))
+    out = ops.transform_two_body(spin, orthonormal)
+    scale = float(out.abs().max())
+    assert float((out + out.permute(0, 1, 3, 2)).abs().max()) <= 1e-12 * scale
+    assert float((out + out.permute(1, 0, 2, 3)).abs().max()) <= 1e-12 * scale
+    assert float((out - out.permute(1, 0, 3, 2)).abs().max()) <= 1e-12 * scale
+
+
+def test_config3_odqd_grid_build_and_fock():
+    """configs[2]: ODQD double well l = 100, G = 2001 -- grid Coulomb build (0.8 GB) and Fock matrices."""
+    from quantum_systems_b200 import ODQD, GeneralOrbitalSystem, SpatialOrbitalSystem
+
+    od = ODQD(100, 20, 2001, potential=ODQD.DWPotential(1.0, 5.0))
+    ref = oracle.odqd_setup_basis(100, 20, 2001, ODQD.DWPotential(1.0, 5.0))
+    u = od.u.cpu().numpy()
+    assert_close_scaled(u, np.ascontiguousarray(ref["u"]), rel=1e-12)
+    spas = SpatialOrbitalSystem(20, od.copy_basis())
+    f = spas.construct_fock_matrix(spas.h, spas.u).cpu().numpy()
+    assert_close_scaled(f, oracle.construct_fock_matrix_spatial(ref["h"], ref["u"], 10), rel=1e-12)
+    od.cast_to_complex_on_spin_doubling = False  # keep the 12.8 GB spin-orbital tensor real
+    gos = GeneralOrbitalSystem(20, od)
+    assert gos.u.dtype == torch.float64 and gos.l == 200
+    # Fock matrix of the spin-doubled system against the restricted one: f_gos = kron(f_spatial, I2)
+    f_gos = gos.construct_fock_matrix(gos.h, gos.u).cpu().numpy()
+    assert_close_scaled(f_gos, np.kron(oracle.construct_fock_matrix_spatial(ref["h"], ref["u"], 10), np.eye(2)), rel=1e-12)
