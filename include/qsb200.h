@@ -175,6 +175,24 @@ int qs_odqd_coulomb(const double* Cmat, const double* grid, double alpha, double
                     int64_t Gp, double* u_out, void* workspace, int64_t workspace_bytes,
                     void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Two-dimensional harmonic-oscillator Coulomb elements (Anisimovas & Matulis 1998)
+ *   u[p,q,r,s] = scale * coulomb_ho(n_p, m_p, n_q, m_q, n_r, m_r, n_s, m_s)
+ * replaces coulomb_ho (quantum_dots/two_dim/coulomb_elements.py:6-92) as driven by
+ * _get_coulomb_elements (quantum_dots/two_dim/two_dim_helper.py:250-268) and get_coulomb_elements_B
+ * (:283-300); `scale` is the sqrt(omega) of TwoDimensionalHarmonicOscillator.setup_basis
+ * (quantum_dots/two_dim/two_dim_ho.py:86-88).  The eight nested loops are collapsed analytically
+ * to table-driven sums carried in double-double arithmetic (see csrc/tdho.cu).
+ *   host_n, host_m : HOST arrays of l radial / angular quantum numbers (n >= 0, n + |m| <= 13)
+ *   u_out          : planes [p_begin, p_end) of the (l,l,l,l) float64 tensor, dense
+ *   workspace      : qs_tdho_coulomb_workspace_bytes() bytes of device memory (tables)
+ * ------------------------------------------------------------------------------------------- */
+int qs_tdho_coulomb_workspace_bytes(const int64_t* host_n, const int64_t* host_m, int64_t l,
+                                    int64_t* bytes);
+int qs_tdho_coulomb(const int64_t* host_n, const int64_t* host_m, int64_t l, double scale,
+                    double* u_out, int64_t p_begin, int64_t p_end, void* workspace,
+                    int64_t workspace_bytes, void* stream);
+
 /* Instrumentation for the benchmark harness.
  *   qs_launch_count        : kernels launched by this library since it was loaded (process-wide).
  *   qs_kernel_timing_enable: 1 = bracket every launch site of a kernel family with CUDA events on
@@ -186,6 +204,7 @@ int qs_odqd_coulomb(const double* Cmat, const double* grid, double alpha, double
 #define QS_FAMILY_SPIN_PASS 1
 #define QS_FAMILY_FOCK 2
 #define QS_FAMILY_EXCHANGE 3
+#define QS_FAMILY_TDHO 4
 int64_t qs_launch_count(void);
 int qs_kernel_timing_enable(int enable);
 int qs_kernel_timing_read(int family, double* host_ms_total, double* host_work_total,

@@ -16,6 +16,14 @@ from .general_orbital_system import GeneralOrbitalSystem
 from .spatial_orbital_system import SpatialOrbitalSystem
 from .random_basis import RandomBasisSet
 from .odqd import ODQD
+from . import two_dim_ho  # noqa: F401
+from .two_dim_ho import (
+    get_coulomb_elements,
+    TwoDimensionalHarmonicOscillator,
+    TwoDimensionalDoubleWell,
+    TwoDimSmoothDoubleWell,
+    TwoDimHarmonicOscB,
+)
 
 __all__ = [
     "BasisSet",
@@ -24,5 +32,10 @@ __all__ = [
     "SpatialOrbitalSystem",
     "RandomBasisSet",
     "ODQD",
+    "TwoDimensionalHarmonicOscillator",
+    "TwoDimensionalDoubleWell",
+    "TwoDimSmoothDoubleWell",
+    "TwoDimHarmonicOscB",
+    "get_coulomb_elements",
     "xp",
 ]

@@ -297,3 +297,30 @@ def fock_gathered(h, direct, exchange, n_occ, scale_direct, scale_exchange, f=No
         float(scale_direct), float(scale_exchange), _ptr(f), _stream(),
     )
     return f
+
+
+def tdho_coulomb(n, m, scale=1.0, planes=None, device=None):
+    """Two-dimensional harmonic-oscillator Coulomb elements ``u[p,q,r,s] = scale * coulomb_ho(nm_p, nm_q,
+    nm_r, nm_s)`` for host integer arrays of radial / angular quantum numbers (reference
+    quantum_dots/two_dim/coulomb_elements.py:6-92 driven by two_dim_helper.py:250-268, :283-300).
+    ``planes=(p0, p1)`` restricts the leading index (multi-GPU shard)."""
+    import numpy as _numpy
+
+    n = _numpy.ascontiguousarray(n, dtype=_numpy.int64)
+    m = _numpy.ascontiguousarray(m, dtype=_numpy.int64)
+    if n.ndim != 1 or n.shape != m.shape or n.size == 0:
+        raise ValueError("n and m must be equally long 1-D integer arrays")
+    l = int(n.size)
+    p0, p1 = (0, l) if planes is None else planes
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    i64p = ctypes.POINTER(ctypes.c_int64)
+    n_ptr, m_ptr = n.ctypes.data_as(i64p), m.ctypes.data_as(i64p)
+    nbytes = ctypes.c_int64(0)
+    _native.call("qs_tdho_coulomb_workspace_bytes", n_ptr, m_ptr, l, ctypes.byref(nbytes))
+    out = torch.empty((p1 - p0, l, l, l), dtype=torch.float64, device=device)
+    owner, ws = _workspace(nbytes.value, device)
+    _native.call(
+        "qs_tdho_coulomb", n_ptr, m_ptr, l, float(scale), _ptr(out), p0, p1, ws, nbytes.value, _stream()
+    )
+    owner.record_stream(torch.cuda.current_stream())
+    return out
