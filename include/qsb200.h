@@ -193,6 +193,29 @@ int qs_tdho_coulomb(const int64_t* host_n, const int64_t* host_m, int64_t l, dou
                     double* u_out, int64_t p_begin, int64_t p_end, void* workspace,
                     int64_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Consumers of the two-body tensor (memory-bound passes on one GPU's leading-index shard).
+ *
+ * qs_extract_block  : out = u[a0:a1, b0:b1, c0:c1, d0:d1] as a dense tensor -- the u[o,o,v,v]-style
+ *                     slicing solvers do with QuantumSystem.o / .v (system.py:47-51).  `u` points at a
+ *                     (planes, n, n, n) slab; a0, a1 are relative to its first plane.
+ * qs_scale_add      : out = alpha x + beta y over `count` elements (y may be NULL; out may alias x) --
+ *                     the sums of QuantumSystem.h_t / u_t (system.py:189-215) and AdiabaticSwitching.u_t
+ *                     = f(t) u (time_evolution_operators/operator.py:182-196).  Complex factors need
+ *                     a complex tensor.
+ * qs_occupied_traces: out6 (DEVICE, 6 doubles) = { tr h[o,o], sum_ij u[i,j,i,j], sum_ij u[i,j,j,i] } as
+ *                     (re, im) pairs, i restricted to planes [p_begin, p_end), i, j < n_occ -- the terms of
+ *                     compute_reference_energy (general_orbital_system.py:75-117,
+ *                     spatial_orbital_system.py:106-148).  `u` points at plane p_begin, h at row 0.
+ * ------------------------------------------------------------------------------------------- */
+int qs_extract_block(const void* u, int dtype, int64_t n, int64_t planes, int64_t a0, int64_t a1,
+                     int64_t b0, int64_t b1, int64_t c0, int64_t c1, int64_t d0, int64_t d1, void* out,
+                     void* stream);
+int qs_scale_add(const void* x, const void* y, int dtype, int64_t count, double alpha_re,
+                 double alpha_im, double beta_re, double beta_im, void* out, void* stream);
+int qs_occupied_traces(const void* h, int h_dtype, const void* u, int u_dtype, int64_t n,
+                       int64_t n_occ, int64_t p_begin, int64_t p_end, double* out6, void* stream);
+
 /* Instrumentation for the benchmark harness.
  *   qs_launch_count        : kernels launched by this library since it was loaded (process-wide).
  *   qs_kernel_timing_enable: 1 = bracket every launch site of a kernel family with CUDA events on

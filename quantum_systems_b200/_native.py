@@ -50,6 +50,9 @@ SIGNATURES = {
     "qs_odqd_coulomb": [_ptr, _ptr, _dbl, _dbl, _i64, _i64, _ptr, _ptr, _i64, _ptr],
     "qs_tdho_coulomb_workspace_bytes": [ctypes.POINTER(_i64), ctypes.POINTER(_i64), _i64, ctypes.POINTER(_i64)],
     "qs_tdho_coulomb": [ctypes.POINTER(_i64), ctypes.POINTER(_i64), _i64, _dbl, _ptr, _i64, _i64, _ptr, _i64, _ptr],
+    "qs_extract_block": [_ptr, _int, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr],
+    "qs_scale_add": [_ptr, _ptr, _int, _i64, _dbl, _dbl, _dbl, _dbl, _ptr, _ptr],
+    "qs_occupied_traces": [_ptr, _int, _ptr, _int, _i64, _i64, _i64, _i64, _ptr, _ptr],
     "qs_launch_count": [],
     "qs_kernel_timing_enable": [_int],
     "qs_kernel_timing_read": [_int, ctypes.POINTER(_dbl), ctypes.POINTER(_dbl), ctypes.POINTER(_i64)],

@@ -324,3 +324,74 @@ def tdho_coulomb(n, m, scale=1.0, planes=None, device=None):
     )
     owner.record_stream(torch.cuda.current_stream())
     return out
+
+
+def _bounds(sl, extent):
+    """``slice`` / ``(start, stop)`` / ``None`` -> (start, stop) with numpy's clipping; unit step only."""
+    if sl is None:
+        return 0, extent
+    if isinstance(sl, slice):
+        start, stop, step = sl.indices(extent)
+        if step != 1:
+            raise ValueError("only unit-step slices are supported")
+        return start, max(stop, start)
+    start, stop = sl
+    return int(start), int(stop)
+
+
+def extract_block(u, a=None, b=None, c=None, d=None):
+    """Dense copy of ``u[a, b, c, d]`` for unit-step slices -- the ``u[o, o, v, v]`` blocks solvers cut out
+    with ``system.o`` / ``system.v`` (reference system.py:47-51).  ``u`` may be a leading-index shard
+    ``(planes, n, n, n)``; ``a`` is then relative to the shard."""
+    u = _device_tensor(u, "u")
+    n = u.shape[-1]
+    if u.dim() != 4 or tuple(u.shape[1:]) != (n, n, n):
+        raise ValueError(f"u must be (planes,n,n,n), got {tuple(u.shape)}")
+    (a0, a1), (b0, b1), (c0, c1), (d0, d1) = _bounds(a, u.shape[0]), _bounds(b, n), _bounds(c, n), _bounds(d, n)
+    out = torch.empty((a1 - a0, b1 - b0, c1 - c0, d1 - d0), dtype=u.dtype, device=u.device)
+    _native.call(
+        "qs_extract_block", _ptr(u), _code(u), n, u.shape[0], a0, a1, b0, b1, c0, c1, d0, d1, _ptr(out), _stream()
+    )
+    return out
+
+
+def scale_add(x, alpha, y=None, beta=0.0, out=None):
+    """``alpha x + beta y`` (``y`` optional) in one pass; ``out`` may be ``x`` itself (reference
+    system.py:189-215, time_evolution_operators/operator.py:182-196)."""
+    x = _device_tensor(x, "x")
+    alpha, beta = complex(alpha), complex(beta)
+    if y is not None:
+        y = _device_tensor(y, "y")
+        if y.shape != x.shape:
+            raise ValueError("x and y must have the same shape")
+    needs_complex = alpha.imag != 0 or beta.imag != 0 or (y is not None and y.dtype != x.dtype)
+    if needs_complex:
+        x = x.to(torch.complex128)
+        y = y.to(torch.complex128) if y is not None else None
+    if out is None:
+        out = torch.empty_like(x)
+    elif out.dtype != x.dtype or out.shape != x.shape or not out.is_contiguous():
+        raise ValueError("out must be a contiguous tensor of the result's shape and dtype")
+    _native.call(
+        "qs_scale_add", _ptr(x), _ptr(y), _code(x), x.numel(), alpha.real, alpha.imag, beta.real, beta.imag,
+        _ptr(out), _stream(),
+    )
+    return out
+
+
+def occupied_traces(h, u, n_occ, planes=None):
+    """``(tr h[o,o], sum_ij u[i,j,i,j], sum_ij u[i,j,j,i])`` over the occupied corner as a complex128 device
+    tensor of three entries (reference general_orbital_system.py:113-117, spatial_orbital_system.py:144-148).
+    ``planes=(p0, p1)``: ``u`` is the leading-index shard holding planes ``[p0, p1)`` and only ``i`` in that
+    range is summed (partial sums of one rank)."""
+    h = _device_tensor(h, "h")
+    u = _device_tensor(u, "u")
+    n = h.shape[0]
+    p0, p1 = (0, n) if planes is None else planes
+    if tuple(h.shape) != (n, n) or tuple(u.shape) != (p1 - p0, n, n, n):
+        raise ValueError(f"h must be (n,n) and u (planes,n,n,n), got {tuple(h.shape)} and {tuple(u.shape)}")
+    out = torch.empty(3, dtype=torch.complex128, device=h.device)
+    _native.call(
+        "qs_occupied_traces", _ptr(h), _code(h), _ptr(u), _code(u), n, int(n_occ), p0, p1, _ptr(out), _stream()
+    )
+    return out

@@ -120,6 +120,34 @@ class CudaEngine:
             sx1, w_inner, sw0, sw1, self._stream(),
         )
 
+    # consumers of a shard (csrc/consumers.cu)
+    def extract_block(self, buf, planes, n, bounds):
+        (a0, a1), (b0, b1), (c0, c1), (d0, d1) = bounds
+        out = torch.empty((a1 - a0, b1 - b0, c1 - c0, d1 - d0), dtype=buf.dtype, device="cuda")
+        _native.call(
+            "qs_extract_block", ctypes.c_void_p(buf.at(0)), _CODES[buf.dtype], n, planes, a0, a1, b0, b1, c0, c1, d0,
+            d1, ctypes.c_void_p(out.data_ptr()), self._stream(),
+        )
+        return out
+
+    def scale_add(self, x, y, count, alpha, beta, out):
+        alpha, beta = complex(alpha), complex(beta)
+        _native.call(
+            "qs_scale_add", ctypes.c_void_p(x.at(0)), ctypes.c_void_p(y.at(0) if y is not None else 0),
+            _CODES[x.dtype], count, alpha.real, alpha.imag, beta.real, beta.imag, ctypes.c_void_p(out.at(0)),
+            self._stream(),
+        )
+
+    def occupied_traces(self, h, buf, n, n_occ, p0, p1):
+        from . import ops
+
+        out = torch.empty(3, dtype=torch.complex128, device="cuda")
+        _native.call(
+            "qs_occupied_traces", ops._ptr(h), ops._code(h), ctypes.c_void_p(buf.at(0)), _CODES[buf.dtype], n,
+            int(n_occ), p0, p1, ctypes.c_void_p(out.data_ptr()), self._stream(),
+        )
+        return out
+
     def quarter_scatter(self, A, X, K, lda, image, m_dtype, W, dests, x_inner, x_mid, sx0, sx1, sx2, w_inner, sw0):
         if X <= 0:
             return
@@ -311,6 +339,83 @@ class ShardedTwoBody:
             ctx.dist.all_gather(parts, padded, group=ctx.group)
         parts = [parts[r][: self.offsets[r + 1] - self.offsets[r]] for r in range(ctx.world)]
         return torch.cat(parts, dim=0)
+
+
+    # -------------------------------------------------------------- consumers
+    def _bounds(self, a, b, c, d):
+        from .ops import _bounds
+
+        n = self.n
+        return _bounds(a, n), _bounds(b, n), _bounds(c, n), _bounds(d, n)
+
+    def extract(self, a=None, b=None, c=None, d=None):
+        """Dense ``u[a, b, c, d]`` (unit-step slices), replicated on every rank -- the ``u[o, o, v, v]``
+        blocks of the solvers.  Each rank cuts its own planes out of its shard (``qs_extract_block``);
+        the pieces are all-gathered (the only communication: the block itself)."""
+        ctx = self.ctx
+        (a0, a1), rest = self._bounds(a, b, c, d)[0], self._bounds(a, b, c, d)[1:]
+        pieces = {}
+        for r in ctx.local_ranks:
+            p0, p1 = self.planes(r)
+            lo, hi = min(max(a0, p0), p1), max(min(a1, p1), p0)
+            hi = max(hi, lo)
+            pieces[r] = ctx.engine.extract_block(self.buffers[r][r], p1 - p0, self.n, ((lo - p0, hi - p0),) + rest)
+        if isinstance(ctx, EmulatedContext):
+            return torch.cat([pieces[r] for r in range(ctx.world)], dim=0)
+        piece = pieces[ctx.rank]
+        padded = torch.zeros((self.block,) + tuple(piece.shape[1:]), dtype=piece.dtype, device=piece.device)
+        padded[: piece.shape[0]] = piece
+        parts = [torch.empty_like(padded) for _ in range(ctx.world)]
+        if padded.is_complex():
+            ctx.dist.all_gather([torch.view_as_real(p) for p in parts], torch.view_as_real(padded), group=ctx.group)
+        else:
+            ctx.dist.all_gather(parts, padded, group=ctx.group)
+        rows = []
+        for r in range(ctx.world):
+            p0, p1 = self.planes(r)
+            rows.append(parts[r][: max(min(a1, p1) - max(a0, p0), 0)])
+        return torch.cat(rows, dim=0)
+
+    def axpby_(self, alpha, other=None, beta=0.0):
+        """In place ``u <- alpha u + beta other`` on every shard (``other`` sharded alike); no communication.
+        ``u_t = f(t) u`` of an adiabatic switching is ``axpby_(f(t))`` on a copy."""
+        if other is not None and (other.n != self.n or other.dtype != self.dtype):
+            raise ValueError("operands must share extent and dtype")
+        alpha, beta = complex(alpha), complex(beta)
+        if self.dtype != torch.complex128 and (alpha.imag != 0 or beta.imag != 0):
+            raise TypeError("complex factor on a real sharded tensor")
+        for r in self.ctx.local_ranks:
+            p0, p1 = self.planes(r)
+            count = (p1 - p0) * self.n**3
+            if count:
+                mine = self.buffers[r][r]
+                self.ctx.engine.scale_add(mine, other.buffers[r][r] if other is not None else None, count, alpha, beta,
+                                          mine)
+        return self
+
+    def copy(self):
+        """A new sharded tensor (own buffers, no spare) with the same contents."""
+        new = ShardedTwoBody.empty(self.ctx, self.n, self.dtype, with_spare=False)
+        for r in self.ctx.local_ranks:
+            p0, p1 = self.planes(r)
+            count = (p1 - p0) * self.n**3
+            if count:
+                self.ctx.engine.scale_add(self.buffers[r][r], None, count, 1.0, 0.0, new.buffers[r][r])
+        self.ctx.barrier()
+        return new
+
+    def occupied_traces(self, h, n_occ):
+        """``(tr h[o,o], sum_ij u[i,j,i,j], sum_ij u[i,j,j,i])`` as Python complex numbers: every rank reduces
+        the occupied rows it owns, then a 6-double all-reduce."""
+        ctx = self.ctx
+        total = None
+        for r in ctx.local_ranks:
+            p0, p1 = self.planes(r)
+            part = ctx.engine.occupied_traces(h, self.buffers[r][r], self.n, n_occ, p0, p1)  # rows [p0, p1) only
+            total = part if total is None else total + part
+        if isinstance(ctx, ProcessContext) and ctx.world > 1:
+            ctx.dist.all_reduce(torch.view_as_real(total), group=ctx.group)
+        return tuple(complex(x) for x in total.cpu().tolist())
 
 
 # ------------------------------------------------------------------------------------------------
@@ -559,6 +664,20 @@ class ShardedBasisSet:
         if self.s is not None:
             self.s = ops.transform_one_body(self.s, C, C_tilde)
         self.u = transform_two_body_sharded(self.u, C, C_tilde)
+
+    def compute_reference_energy(self, n_occ, h=None, u=None, nuclear_repulsion_energy=0.0):
+        """``E_0 = h_ii + 1/2 u_ijij + E_n`` over the occupied spin-orbitals (reference
+        general_orbital_system.py:75-117) for a spin-orbital basis, ``2 h_ii + 2 u_ijij - u_ijji + E_n``
+        (spatial_orbital_system.py:106-148) for a spatial one."""
+        h = self.h if h is None else h
+        u = self.u if u is None else u
+        tr_h, direct, exchange = u.occupied_traces(h, n_occ)
+        if self.includes_spin:
+            energy = tr_h + 0.5 * direct + nuclear_repulsion_energy
+        else:
+            energy = 2 * tr_h + 2 * direct - exchange + nuclear_repulsion_energy
+        is_complex = u.dtype == torch.complex128 or h.is_complex()
+        return energy if is_complex else energy.real
 
     def construct_fock_matrix(self, h, u, n_occ, f=None):
         """``f = h + sum_i u[p,i,q,i]``: every rank reduces the rows p it owns, then the rows are

@@ -158,11 +158,26 @@ class QuantumSystem(metaclass=abc.ABCMeta):
 
     # helpers shared by the concrete systems -----------------------------------------------
     def _occupied_trace_terms(self, h, u):
-        """``tr h[o,o]``, ``sum_ij u[i,j,i,j]``, ``sum_ij u[i,j,j,i]`` on the n_occ^4 corner (tiny)."""
-        np = self.np
-        o = self.o
-        h_oo = h[o, o]
-        u_oooo = u[o, o, o, o]
-        direct = np.trace(np.trace(u_oooo, axis1=1, axis2=3))
-        exchange = np.trace(np.trace(u_oooo, axis1=1, axis2=2))
-        return np.trace(h_oo), direct, exchange
+        """``tr h[o,o]``, ``sum_ij u[i,j,i,j]``, ``sum_ij u[i,j,j,i]`` as Python scalars, reduced on the GPU
+        (``ops.occupied_traces``).  Host arrays: only the occupied corner (n_occ^4 elements) is staged."""
+        import numpy
+        import torch
+
+        from . import _arrays, ops
+
+        n_occ = self.n
+        if n_occ == 0:
+            return 0.0, 0.0, 0.0
+        if isinstance(u, torch.Tensor) and u.is_cuda:
+            terms = ops.occupied_traces(_arrays.to_device(h), u, n_occ)
+            is_complex = u.is_complex() or (h.is_complex() if isinstance(h, torch.Tensor) else numpy.iscomplexobj(h))
+        else:
+            o = self.o
+            corner = _arrays.to_device(numpy.ascontiguousarray(u[o, o, o, o]))
+            h_oo = _arrays.to_device(numpy.ascontiguousarray(h[o, o]))
+            terms = ops.occupied_traces(h_oo, corner, n_occ)
+            is_complex = numpy.iscomplexobj(u) or numpy.iscomplexobj(h)
+        tr_h, direct, exchange = (complex(x) for x in terms.cpu().tolist())
+        if not is_complex:
+            tr_h, direct, exchange = tr_h.real, direct.real, exchange.real
+        return tr_h, direct, exchange

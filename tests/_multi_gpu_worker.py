@@ -51,6 +51,16 @@ def main():
         f = basis.construct_fock_matrix(basis.h, basis.u, n_occ).cpu().numpy()
         ref_f = oracle.construct_fock_matrix_general(ref_h, ref_u, n_occ)
         assert np.abs(f - ref_f).max() <= 1e-12 * np.abs(ref_f).max()
+        # consumers of the sharded result: replicated o/v blocks, reference energy, scaled copy
+        o, v = slice(0, n_occ), slice(n_occ, 2 * l)
+        scale = np.abs(ref_u).max()
+        assert np.abs(basis.u.extract(o, o, v, v).cpu().numpy() - ref_u[o, o, v, v]).max() <= 1e-12 * scale
+        assert np.abs(basis.u.extract(v, o, None, o).cpu().numpy() - ref_u[v, o, :, o]).max() <= 1e-12 * scale
+        e_ref = oracle.reference_energy_general(ref_h, ref_u, n_occ)
+        assert abs(basis.compute_reference_energy(n_occ) - e_ref) <= 1e-11 * abs(e_ref)
+        q0, q1 = basis.u.planes(rank)
+        doubled = basis.u.copy().axpby_(2.0)
+        assert np.abs(doubled.local().cpu().numpy() - 2.0 * ref_u[q0:q1]).max() <= 2e-12 * scale
         torch.cuda.synchronize()
         dist.barrier()
         if rank == 0:

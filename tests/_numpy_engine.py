@@ -74,3 +74,28 @@ class NumpyEngine:
                 continue
             aw = (cols % w_inner) * sw0
             buf.flat()[off + ax[:, None] + aw[None, :]] = res[:, cols]
+
+    # consumers of a shard: documented semantics of qs_extract_block / qs_scale_add / qs_occupied_traces
+    def extract_block(self, buf, planes, n, bounds):
+        (a0, a1), (b0, b1), (c0, c1), (d0, d1) = bounds
+        slab = buf.flat()[: planes * n**3].reshape(planes, n, n, n)
+        return torch.from_numpy(np.ascontiguousarray(slab[a0:a1, b0:b1, c0:c1, d0:d1]))
+
+    def scale_add(self, x, y, count, alpha, beta, out):
+        if not x.dtype.is_complex:
+            alpha, beta = complex(alpha).real, complex(beta).real
+        res = alpha * x.flat()[:count]
+        if y is not None:
+            res = res + beta * y.flat()[:count]
+        out.flat()[:count] = res
+
+    def occupied_traces(self, h, buf, n, n_occ, p0, p1):
+        h = h.numpy() if isinstance(h, torch.Tensor) else np.asarray(h)
+        slab = buf.flat()[: (p1 - p0) * n**3].reshape(p1 - p0, n, n, n)
+        tr_h = direct = exchange = 0.0
+        for i in range(p0, min(p1, n_occ)):
+            tr_h += h[i, i]
+            for j in range(n_occ):
+                direct += slab[i - p0, j, i, j]
+                exchange += slab[i - p0, j, j, i]
+        return torch.tensor([tr_h, direct, exchange], dtype=torch.complex128)

@@ -65,6 +65,41 @@ def test_emulated_peer_schedule_matches_oracle(world, n, m, u_complex, c_complex
         np.testing.assert_allclose(out2.gather().numpy(), expected2, rtol=1e-11, atol=1e-11 * np.abs(expected2).max())
 
 
+@pytest.mark.parametrize("world", [1, 2, 3, 5])
+@pytest.mark.parametrize("complex_", [False, True])
+def test_emulated_consumers_of_a_sharded_tensor(world, complex_):
+    """u[o,o,v,v]-style blocks, scaled copies and the reference energy on a sharded tensor
+     against plain numpy slicing and the oracle."""
+    from quantum_systems_b200 import sharded
+
+    n, n_occ = 7, 3
+    rng = np.random.default_rng(17 + world)
+    u = rand(rng, (n,) * 4, complex_)
+    h = rand(rng, (n, n), complex_)
+    ctx = sharded.EmulatedContext(world, engine=NumpyEngine())
+    basis = sharded.ShardedBasisSet.from_global(ctx, h, np.eye(n), u, includes_spin=True)
+    o, v = slice(0, n_occ), slice(n_occ, n)
+    for sl in [(o, o, v, v), (v, o, v, o), (o, o, o, o), (v, v, v, v), (slice(2, 6), None, slice(0, 1), v),
+               (slice(5, 5), o, o, o)]:
+        np.testing.assert_array_equal(basis.u.extract(*sl).numpy(), u[tuple(slice(None) if s is None else s for s in sl)])
+    np.testing.assert_allclose(
+        basis.compute_reference_energy(n_occ, nuclear_repulsion_energy=0.25),
+        oracle.reference_energy_general(h, u, n_occ, 0.25), rtol=1e-13,
+    )
+    spatial = sharded.ShardedBasisSet.from_global(ctx, h, np.eye(n), u)
+    np.testing.assert_allclose(
+        spatial.compute_reference_energy(n_occ), oracle.reference_energy_spatial(h, u, n_occ), rtol=1e-13
+    )
+    scaled = basis.u.copy().axpby_(0.5)
+    np.testing.assert_array_equal(scaled.gather().numpy(), 0.5 * u)
+    np.testing.assert_array_equal(basis.u.gather().numpy(), u)  # the copy left the original alone
+    combo = basis.u.copy().axpby_(2.0, scaled, -3.0)
+    np.testing.assert_allclose(combo.gather().numpy(), 2.0 * u - 1.5 * u, rtol=1e-15)
+    if not complex_:
+        with pytest.raises(TypeError):
+            basis.u.axpby_(1j)
+
+
 def _free_port():
     with socket.socket() as sock:
         sock.bind(("127.0.0.1", 0))
@@ -94,6 +129,20 @@ def _gloo_worker(rank, world, port, n, m, complex_, results):
         np.testing.assert_allclose(out.local().numpy(), expected[q0:q1], rtol=1e-12, atol=1e-12 * np.abs(expected).max())
         full = out.gather().numpy()
         np.testing.assert_allclose(full, expected, rtol=1e-12, atol=1e-12 * np.abs(expected).max())
+        # consumers: replicated blocks (all-gather) and the reference energy (6-double all-reduce)
+        if m >= 4:
+            o, v = slice(0, 3), slice(3, m)
+            np.testing.assert_allclose(out.extract(o, o, v, v).numpy(), expected[o, o, v, v], rtol=1e-12,
+                                       atol=1e-12 * np.abs(expected).max())
+            np.testing.assert_allclose(out.extract(v, o, None, o).numpy(), expected[v, o, :, o], rtol=1e-12,
+                                       atol=1e-12 * np.abs(expected).max())
+            h = rand(np.random.default_rng(3), (m, m), complex_)
+            holder = sharded.ShardedBasisSet(ctx, m, torch.from_numpy(h), None, out, includes_spin=True)
+            np.testing.assert_allclose(holder.compute_reference_energy(3), oracle.reference_energy_general(h, expected, 3),
+                                       rtol=1e-11)
+            doubled = out.copy().axpby_(2.0)
+            np.testing.assert_allclose(doubled.local().numpy(), 2.0 * expected[q0:q1], rtol=1e-12,
+                                       atol=1e-12 * np.abs(expected).max())
         results[rank] = "ok"
     finally:
         dist.destroy_process_group()
