@@ -88,6 +88,19 @@ int qs_quarter_transform_scatter(const void* A, int a_dtype, int64_t X, int64_t 
                                  int64_t x_mid, int64_t sx0, int64_t sx1, int64_t sx2,
                                  int64_t w_inner, int64_t sw0, void* stream);
 
+/* Four-index transform of an operator that is diagonal in the original basis, u[a,b,c,d] = W[a,b] d_ac d_bd
+ * (the sinc-DVR storage u_repr = "2d"):
+ *   out[p,q,r,s] = sum_ab Ct[p,a] C[a,r] Ct[q,b] C[b,s] W[a,b]   ( - out[p,q,s,r] if anti_symmetrize )
+ * replaces the einsum of ODSincDVR.transform_two_body_elements (sinc_dvr/one_dim/sinc_dvr.py:217-252) with
+ * two chained DMMA GEMMs, O(m^4 n) instead of O(n^5).
+ *   w2d : (n, n) dtype w_dtype;  C : (n, m);  Ct : (m, n) or NULL for conj(C)^T;  out : (m,m,m,m), complex128 if
+ *   W or C is complex, else float64.  workspace: qs_transform_two_body_diagonal_workspace_bytes(), 1 KiB aligned. */
+int qs_transform_two_body_diagonal_workspace_bytes(int64_t n, int64_t m, int w_dtype, int c_dtype,
+                                                   int anti_symmetrize, int64_t* bytes);
+int qs_transform_two_body_diagonal(const void* w2d, int w_dtype, const void* C, const void* Ct,
+                                   int c_dtype, int64_t n, int64_t m, int anti_symmetrize, void* out,
+                                   void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Copy `rows` rows of n elements into rows of `pitch` >= n elements, zero-filling the tail (real
  * tensors with odd n need an even pitch before they can be described to TMA). */
 int qs_pad_rows(const void* in, void* out, int64_t rows, int64_t n, int64_t pitch, int dtype,

@@ -319,3 +319,54 @@ def odqd_setup_basis(l, grid_length, num_grid_points, potential, a=0.25, alpha=1
         "u": odqd_coulomb_elements(C, grid, alpha, a),
         "position": position,
     }
+
+
+# --------------------------------------------------------------------------------------------
+# one-dimensional sinc-DVR (two-body operator diagonal in the basis)
+# --------------------------------------------------------------------------------------------
+
+
+def sinc_dvr_setup_basis(l, grid_length, potential, a=0.25, alpha=1.0, beta=0.0, u_repr="2d"):
+    """Everything ``ODSincDVR.setup_basis`` stores -- sinc_dvr/one_dim/sinc_dvr.py:99-127, :146-176.
+    ``u`` is the (l, l) matrix of shielded-Coulomb values for ``u_repr="2d"`` or the (l,l,l,l) tensor
+    with ``u[p,q,p,q] = W[p,q]`` for ``"4d"``; every array is cast to complex128 at the end (:126)."""
+    grid = np.linspace(-grid_length, grid_length, l)
+    dx = grid[1] - grid[0]
+    ind = np.arange(l)
+    diff = ind[:, None] - ind
+    h = np.zeros((l, l), dtype=np.complex128)
+    off = ~np.eye(l, dtype=bool)
+    h[off] = (-1.0) ** diff[off] / (dx**2 * diff[off] ** 2)  # :108-113
+    h[ind, ind] = np.pi**2 / (6 * dx**2) + potential(grid)  # :115-116
+    spf = 1 / np.sqrt(dx) * np.sinc((grid - grid[:, None]) / dx)  # :146-148
+    w = shielded_coulomb(grid[:, None], grid[None, :], alpha, a)  # :160-165
+    if u_repr == "2d":
+        u = w
+    else:
+        u = np.zeros((l, l, l, l))
+        u[ind[:, None], ind[None, :], ind[:, None], ind[None, :]] = w  # :171-173
+    position = np.zeros((1, l, l), dtype=np.complex128)
+    position[0] = np.diag(grid + beta * grid**2)  # :150-152
+    return {
+        "grid": grid,
+        "h": h,
+        "s": np.eye(l).astype(np.complex128),
+        "spf": spf.astype(np.complex128),
+        "u": u.astype(np.complex128),
+        "position": position,
+    }
+
+
+def sinc_dvr_transform_two_body_elements(u2d, C, C_tilde=None, anti_symmetrize=False):
+    """``u'_pqrs = sum_ab C~_pa C_ar C~_qb C_bs u_ab`` (minus the r <-> s exchange) --
+    sinc_dvr/one_dim/sinc_dvr.py:225-252, the same einsum strings."""
+    bra = default_bra_coefficients(C) if C_tilde is None else C_tilde
+    out = np.einsum("bs,ar,qb,pa,ab->pqrs", C, C, bra, bra, u2d, optimize=True)
+    if anti_symmetrize:
+        out = out - np.einsum("br,as,qb,pa,ab->pqrs", C, C, bra, bra, u2d, optimize=True)
+    return out
+
+
+def sinc_dvr_add_spin_two_body(u2d):
+    """``kron(u, ones(2, 2))`` for the 2-D representation -- sinc_dvr.py:200-208."""
+    return np.kron(u2d, np.ones((2, 2)))

@@ -16,6 +16,7 @@ from .general_orbital_system import GeneralOrbitalSystem
 from .spatial_orbital_system import SpatialOrbitalSystem
 from .random_basis import RandomBasisSet
 from .odqd import ODQD
+from .sinc_dvr import ODSincDVR
 from . import two_dim_ho  # noqa: F401
 from .two_dim_ho import (
     get_coulomb_elements,
@@ -32,6 +33,7 @@ __all__ = [
     "SpatialOrbitalSystem",
     "RandomBasisSet",
     "ODQD",
+    "ODSincDVR",
     "TwoDimensionalHarmonicOscillator",
     "TwoDimensionalDoubleWell",
     "TwoDimSmoothDoubleWell",

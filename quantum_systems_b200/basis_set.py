@@ -419,10 +419,21 @@ class BasisSet:
         self.h = self.add_spin_one_body(self.h, np=self.np)
         self.s = self.add_spin_one_body(self.s, np=self.np)
 
-        fuse_as = bool(anti_symmetrize) and not self._anti_symmetrized_u
-        u_dev = _arrays.to_device(self._u)
-        out_dtype = torch.complex128 if (widen or u_dev.is_complex()) else torch.float64
-        self.u = _arrays.to_module(ops.add_spin_two_body(u_dev, anti_symmetrize=fuse_as, out_dtype=out_dtype), self.np)
+        # A subclass that overrides the static hooks (reference dispatch through `self`, basis_set.py:523, :576;
+        # e.g. the 2-D sinc-DVR storage) gets its own add_spin_two_body / anti_symmetrize_u, un-fused.
+        hooks_overridden = (
+            type(self).add_spin_two_body is not BasisSet.add_spin_two_body
+            or type(self).anti_symmetrize_u is not BasisSet.anti_symmetrize_u
+        )
+        fuse_as = bool(anti_symmetrize) and not self._anti_symmetrized_u and not hooks_overridden
+        if hooks_overridden:
+            self.u = self.add_spin_two_body(self._u, np=self.np)
+        else:
+            u_dev = _arrays.to_device(self._u)
+            out_dtype = torch.complex128 if (widen or u_dev.is_complex()) else torch.float64
+            self.u = _arrays.to_module(
+                ops.add_spin_two_body(u_dev, anti_symmetrize=fuse_as, out_dtype=out_dtype), self.np
+            )
 
         if getattr(self, "u_repr", "4d") != "2d":
             np_host = _host_numpy()

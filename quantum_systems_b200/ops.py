@@ -395,3 +395,27 @@ def occupied_traces(h, u, n_occ, planes=None):
         "qs_occupied_traces", _ptr(h), _code(h), _ptr(u), _code(u), n, int(n_occ), p0, p1, _ptr(out), _stream()
     )
     return out
+
+
+def transform_two_body_diagonal(w2d, C, C_tilde=None, anti_symmetrize=False):
+    """``u'_pqrs = sum_ab C~[p,a] C[a,r] C~[q,b] C[b,s] W[a,b]`` for a two-body operator stored by its
+    diagonal ``W`` (sinc-DVR ``u_repr = "2d"``), optionally minus the ``r <-> s`` exchange (reference
+    sinc_dvr/one_dim/sinc_dvr.py:217-252)."""
+    w2d = _device_tensor(w2d, "u (2d)")
+    C, C_tilde = _coefficients(C, C_tilde)
+    n, m = C.shape
+    if tuple(w2d.shape) != (n, n):
+        raise ValueError(f"the 2d two-body operator must be {(n, n)}, got {tuple(w2d.shape)}")
+    out = torch.empty((m, m, m, m), dtype=_result_dtype(w2d, C), device=w2d.device)
+    nbytes = ctypes.c_int64(0)
+    _native.call(
+        "qs_transform_two_body_diagonal_workspace_bytes", n, m, _code(w2d), _code(C), int(bool(anti_symmetrize)),
+        ctypes.byref(nbytes),
+    )
+    owner, ws = _workspace(nbytes.value, w2d.device)
+    _native.call(
+        "qs_transform_two_body_diagonal", _ptr(w2d), _code(w2d), _ptr(C), _ptr(C_tilde), _code(C), n, m,
+        int(bool(anti_symmetrize)), _ptr(out), ws, nbytes.value, _stream(),
+    )
+    owner.record_stream(torch.cuda.current_stream())
+    return out

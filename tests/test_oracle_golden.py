@@ -162,3 +162,32 @@ def test_config1_sample():
     np.testing.assert_allclose(np.abs(out["u"]).max(), float(g["u_max"]), rtol=1e-9)
     np.testing.assert_allclose(out["h"], g["h"], atol=1e-10)
     np.testing.assert_allclose(out["u"][np.ix_(idx, idx, idx, idx)], g["u_sample"], atol=1e-10)
+
+
+# --------------------------------------------------------------------------------------------
+# sinc-DVR (reference-run vectors; the reference has no test of this class)
+# --------------------------------------------------------------------------------------------
+
+
+def test_sinc_dvr_oracle_matches_reference_run():
+    from quantum_systems_b200 import potentials
+
+    g = load_golden("sinc_dvr_reference_run")
+    for repr_ in ("2d", "4d"):
+        basis = oracle.sinc_dvr_setup_basis(
+            14, 6.0, potentials.DWPotential(1.0, 2.0), a=0.3, alpha=0.9, beta=0.1, u_repr=repr_
+        )
+        for key in ("h", "s", "u", "spf", "position"):
+            assert basis[key].dtype == g[f"{repr_}_{key}"].dtype
+            np.testing.assert_allclose(basis[key], g[f"{repr_}_{key}"], atol=1e-14, rtol=0)
+    w, C, Ct = g["2d_u"], g["C"], g["Ct"]
+    np.testing.assert_allclose(oracle.sinc_dvr_transform_two_body_elements(w, C), g["tb_default"], atol=1e-12)
+    np.testing.assert_allclose(oracle.sinc_dvr_transform_two_body_elements(w, C, Ct), g["tb_biorth"], atol=1e-12)
+    np.testing.assert_allclose(
+        oracle.sinc_dvr_transform_two_body_elements(w, C, Ct, anti_symmetrize=True), g["tb_antisym"], atol=1e-12
+    )
+    np.testing.assert_allclose(oracle.sinc_dvr_transform_two_body_elements(w, g["Cr"]), g["tb_real_C"], atol=1e-12)
+    # the structured transform equals the dense four-index transform of the 4-D representation
+    np.testing.assert_allclose(oracle.transform_two_body_elements(g["4d_u"], C, Ct), g["tb_biorth"], atol=1e-11)
+    np.testing.assert_allclose(g["tb_dense_4d"], g["tb_biorth"], atol=1e-11)
+    np.testing.assert_array_equal(oracle.sinc_dvr_add_spin_two_body(np.arange(4.0).reshape(2, 2))[:2, :2], np.zeros((2, 2)))
