@@ -50,7 +50,8 @@ def main():
     gathered = [None] * world
     dist.all_gather_object(gathered, res)
     if rank == 0:
-        print(json.dumps({"n": n, "world": world, "rank0": gathered[0], "rank_last": gathered[-1]}))
+        table = {k: [g[k] for g in gathered] for k in names + ["total"]}
+        print(json.dumps({"n": n, "world": world, "per_rank_ms": table, "rank0": gathered[0], "rank_last": gathered[-1]}))
     ctx.close()
     dist.destroy_process_group()
 
