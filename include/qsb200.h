@@ -81,12 +81,22 @@ int qs_quarter_transform(const void* A, int a_dtype, int64_t X, int64_t K, int64
  * index is split three ways, x = (x2 * x_mid + x1) * x_inner + x0, and contributes
  * x2 * sx2 + x1 * sx1 + x0 * sx0, so a shard's planes land between the planes of the other ranks.
  * One launch computes the quarter step AND delivers every tile to the GPU that owns it over
- * NVLink -- the all-to-all of SURVEY.md section 8e without a second pass over memory. */
+ * NVLink -- the all-to-all of SURVEY.md section 8e without a second pass over memory.
+ *
+ * Column dealing.  With contiguous column ranges per CTA tile every rank writes to the same one or two
+ * peers at any moment (an NVLink ingress hot spot: +29 % on 7 of 8 ranks at n = 400).  `w_deal` > 1
+ * (from qs_scatter_deal(W)) makes the j-th column of the tile order the PHYSICAL column (j * w_deal) % W,
+ * spreading every tile over all destinations; the image must then come from qs_build_coeff_image_dealt
+ * with the same multiplier.  w_deal = 1: columns in natural order (plain qs_build_coeff_image). */
+int qs_scatter_deal(int64_t W, int64_t* w_deal);
+int qs_build_coeff_image_dealt(const void* m, int m_dtype, int64_t m_sk, int64_t m_sw, int m_conj,
+                               int64_t K, int64_t W, int a_dtype, int64_t w_deal, void* image,
+                               void* stream);
 int qs_quarter_transform_scatter(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda,
                                  const void* image, int m_dtype, int64_t W,
                                  void* const* host_out_table, int64_t n_dest, int64_t x_inner,
                                  int64_t x_mid, int64_t sx0, int64_t sx1, int64_t sx2,
-                                 int64_t w_inner, int64_t sw0, void* stream);
+                                 int64_t w_inner, int64_t sw0, int64_t w_deal, void* stream);
 
 /* Four-index transform of an operator that is diagonal in the original basis, u[a,b,c,d] = W[a,b] d_ac d_bd
  * (the sinc-DVR storage u_repr = "2d"):

@@ -61,7 +61,16 @@ struct QuarterParams {
     uint32_t x_inner, x_mid, w_inner;
     long long sx0, sx1, sx2, sw0, sw1;
     int vec2;                 // real output: row pairs (x, x + 1), x even, are adjacent and 16-byte aligned
+    // Column dealing (scattering store): logical output column j of the tile order is the physical column
+    // (j * deal_mul) % deal_mod, so every CTA tile's columns are spread over ALL destinations and the NVLink
+    // traffic of a launch is uniform in time (contiguous column ranges make every rank write to the same one or
+    // two peers at once: measured +29 % on 7 of 8 ranks at n = 400).  deal_mul == 1: identity.
+    uint32_t deal_mul, deal_mod;
 };
+
+__device__ __forceinline__ uint32_t dealt_column(uint32_t w, uint32_t mul, uint32_t mod) {
+    return mul == 1 ? w : (uint32_t)(((unsigned long long)w * mul) % mod);
+}
 
 #ifdef QS_DBG_NOWAIT
 #define QS_FULL_WAIT(bar, par) ((void)0)
@@ -343,7 +352,7 @@ quarter_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             const uint32_t wp = wbase + 8 * nt + 2 * t;  // real column of acc[..][nt][0]; wp + 1 for [1]
             if (COMPLEX_OUT) {
                 if (wp < p.Wp) {
-                    const uint32_t w = wp >> 1;
+                    const uint32_t w = dealt_column(wp >> 1, p.deal_mul, p.deal_mod);
                     double* col;
                     if (plain_w) {
                         col = p.out + 2 * ((long long)w * p.sw1);
@@ -360,8 +369,8 @@ quarter_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             } else {
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const uint32_t w = wp + e;
-                    if (w < p.Wp) {
+                    if (wp + e < p.Wp) {
+                        const uint32_t w = dealt_column(wp + e, p.deal_mul, p.deal_mod);
                         double* col;
                         if (plain_w) {
                             col = p.out + (long long)w * p.sw1;
@@ -386,6 +395,227 @@ quarter_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Split variant: complex A times REAL M ("2M").  Z = (Ar + i Ai) M = Ar M + i Ai M is two real products with
+// the SAME coefficient fragments; lowering it to the generic kernel through the real image [[M, 0], [0, M]]
+// would issue twice the DMMAs, half of them on zeros.  Here a lane's A fragment double2 is (re, im) of one
+// complex k (interleaved storage, as in the generic kernel): the .x halves feed the accumulators of the real
+// parts, the .y halves those of the imaginary parts, both against one B fragment per (k, column) taken from an
+// image that stores M once:  image[tile][chunk][ntc][lane][h] = M[8 chunk + 4h + t][w_first + 8 NTC tile + 8 ntc + g].
+// Same CTA organisation as quarter_gemm_kernel (two ordered MMA groups, per-group TMA producer and ring,
+// setmaxnreg split); a CTA tile is 128 rows x 8 NTC complex columns (NTC <= 4).
+// ---------------------------------------------------------------------------------------------
+template <int NTC>
+struct SplitRing {
+    static constexpr int kBTileBytes = NTC * 512;  // 8 complex k x 8*NTC columns, one double each
+    static constexpr int kStageBytes = kATileBytes + kBTileBytes;
+    static constexpr int kFit = (110 * 1024) / kStageBytes;
+    static constexpr int kStages = kFit < 6 ? kFit : 6;
+    static constexpr int kRingBytes = kStages * kStageBytes;
+    static constexpr int kSmemBytes = kGroups * kRingBytes + (kGroups * 2 * kStages + 2) * 8 + 1024;
+};
+
+template <int NTC>
+__global__ void __launch_bounds__(kThreads, 1)
+quarter_gemm_split_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ QuarterParams p) {
+    using Ring = SplitRing<NTC>;
+    constexpr int kBTileBytes = Ring::kBTileBytes;
+    constexpr int kStageBytes = Ring::kStageBytes;
+    constexpr int kStages = Ring::kStages;
+
+    extern __shared__ unsigned char smem_raw[];
+    uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    asm volatile("" : "+r"(smem_base));
+    const uint32_t bar_base = smem_base + kGroups * Ring::kRingBytes;
+    const uint32_t bar_order = bar_base + kGroups * 2 * kStages * 8;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t total_tiles = p.tiles_x * (uint32_t)p.tiles_w;
+    const uint32_t my_tiles = blockIdx.x < total_tiles ? (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (threadIdx.x == 0) {
+        for (int gs = 0; gs < kGroups * kStages; ++gs) {
+            const uint32_t base = bar_base + (gs / kStages) * 16 * kStages + (gs % kStages) * 8;
+            mbar_init(base, 1);
+            mbar_init(base + 8 * kStages, kGroupWarps);
+        }
+        mbar_init(bar_order, kGroupWarps);
+        mbar_init(bar_order + 8, kGroupWarps);
+        mbar_fence_init();
+        prefetch_tensormap(&map_a);
+    }
+    __syncthreads();
+
+    if (warp >= kMmaWarps) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsProducer));
+        const int pg = warp - kMmaWarps;
+        if (pg >= kGroups) return;
+        if (lane == 0) {
+            const uint32_t ring = smem_base + pg * Ring::kRingBytes;
+            const uint32_t bar_full = bar_base + pg * 16 * kStages;
+            const uint32_t bar_empty = bar_full + 8 * kStages;
+            uint32_t j = 0;
+            for (uint32_t i = pg; i < my_tiles; i += kGroups) {
+                const uint32_t tile = blockIdx.x + i * gridDim.x;
+                const uint32_t tw = tile % (uint32_t)p.tiles_w;
+                const int px0 = (int)((tile / (uint32_t)p.tiles_w) * kBlockX);
+                const double* img = p.image + (size_t)tw * p.nchunks * (kBTileBytes / 8);
+                for (int c = 0; c < p.nchunks; ++c, ++j) {
+                    const uint32_t s = j % kStages;
+                    if (j >= (uint32_t)kStages) mbar_wait(bar_empty + 8 * s, ((j / kStages) - 1) & 1);
+                    const uint32_t full = bar_full + 8 * s;
+                    mbar_expect_tx(full, kStageBytes);
+                    const uint32_t dst = ring + s * kStageBytes;
+                    tma_load_2d(dst, &map_a, c * kChunkK, px0, full);
+                    bulk_load_1d(dst + kATileBytes, img + (size_t)c * (kBTileBytes / 8), kBTileBytes, full);
+                }
+            }
+        }
+        return;
+    }
+
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsMma));
+    const int group = warp >> 2;
+    const int wg = warp & 3;
+    const uint32_t ring = smem_base + group * Ring::kRingBytes;
+    const uint32_t bar_full = bar_base + group * 16 * kStages;
+    const uint32_t bar_empty = bar_full + 8 * kStages;
+    const int g = lane >> 2;
+    const int t = lane & 3;
+    const int rbase = row_base(g);
+    const uint32_t a_row_off = (uint32_t)(32 * wg + rbase) * 128u;
+    const uint32_t b_lane_off = kATileBytes + (uint32_t)lane * 16u;
+    auto a_frag_off = [&](int mt, int h) {
+        return a_row_off + (uint32_t)((mt & 1) * 128 + (mt >> 1) * 2048) +
+               (uint32_t)(((4 * h + t) ^ ((rbase & 7) | (mt & 1))) << 4);
+    };
+    auto load_a = [&](double2(&a)[4], uint32_t stage, int h) {
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) a[mt] = lds_128(stage + a_frag_off(mt, h));
+    };
+    auto load_b = [&](double2(&b)[NTC], uint32_t stage) {
+#pragma unroll
+        for (int ntc = 0; ntc < NTC; ++ntc) b[ntc] = lds_128(stage + b_lane_off + (uint32_t)ntc * 512u);
+    };
+
+    for (uint32_t i = group; i < my_tiles; i += kGroups) {
+        const uint32_t tile = blockIdx.x + i * gridDim.x;
+
+        double re[4][NTC][2], im[4][NTC][2];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int ntc = 0; ntc < NTC; ++ntc) re[mt][ntc][0] = re[mt][ntc][1] = im[mt][ntc][0] = im[mt][ntc][1] = 0.0;
+
+        // one half chunk (4 complex k): real parts of A against b, then imaginary parts against the same b
+        auto half_step = [&](const double2(&a)[4], const double2(&b)[NTC], bool second) {
+#pragma unroll
+            for (int ntc = 0; ntc < NTC; ++ntc)
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt)
+                    dmma_8x8x4(re[mt][ntc][0], re[mt][ntc][1], a[mt].x, second ? b[ntc].y : b[ntc].x);
+#pragma unroll
+            for (int ntc = 0; ntc < NTC; ++ntc)
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt)
+                    dmma_8x8x4(im[mt][ntc][0], im[mt][ntc][1], a[mt].y, second ? b[ntc].y : b[ntc].x);
+        };
+
+        const uint32_t j = (i >> 1) * (uint32_t)p.nchunks;
+        uint32_t s = j % kStages, par = (j / kStages) & 1;
+        uint32_t stage = ring + s * kStageBytes;
+        double2 a0[4], a1[4], b0[NTC], b1[NTC];
+        mbar_wait(bar_full + 8 * s, par);
+        load_a(a0, stage, 0);
+        load_b(b0, stage);
+
+        const uint32_t k = i >> 1;
+        if (i > 0) mbar_wait(bar_order + 8 * group, (group == 0 ? k - 1 : k) & 1);
+        const int signal_chunk = (p.nchunks - 1) >> 1;
+
+        // chunks are processed in pairs of register sets (a0/b0 <-> a1's successor) without copies: the loop
+        // body is written once for "current = (a0, b0)" and the fragments of the next chunk land in (a0, b1) ...
+        for (int c = 0; c + 1 < p.nchunks; ++c) {
+            load_a(a1, stage, 1);           // second half of this chunk, in flight during the first half's DMMAs
+            half_step(a0, b0, false);
+            const uint32_t s_done = s;
+            if (++s == (uint32_t)kStages) {
+                s = 0;
+                par ^= 1;
+            }
+            const uint32_t next_stage = ring + s * kStageBytes;
+            mbar_wait(bar_full + 8 * s, par);
+            load_a(a0, next_stage, 0);      // first half of the next chunk, in flight during the second half
+            load_b(b1, next_stage);
+            half_step(a1, b0, true);
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(bar_empty + 8 * s_done);
+                if (c == signal_chunk) mbar_arrive(bar_order + 8 * (group ^ 1));
+            }
+#pragma unroll
+            for (int ntc = 0; ntc < NTC; ++ntc) b0[ntc] = b1[ntc];
+            stage = next_stage;
+        }
+        // last chunk: it may hold <= 4 valid complex k, then its all-zero second half is skipped
+        if (p.last_halves == 2) load_a(a1, stage, 1);
+        half_step(a0, b0, false);
+        if (p.last_halves == 2) half_step(a1, b0, true);
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(bar_empty + 8 * s);
+            if (signal_chunk == p.nchunks - 1) mbar_arrive(bar_order + 8 * (group ^ 1));
+        }
+
+        // ===== epilogue: complex128 (re, im) pairs, rotated / strided / scattering store =====
+        const uint32_t tile_w = tile % (uint32_t)p.tiles_w;
+        const uint32_t x0 = (tile / (uint32_t)p.tiles_w) * kBlockX;
+        long long xoff[4];
+        bool xok[4];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+            const uint32_t x = x0 + 32 * wg + rbase + (mt & 1) + 16 * (mt >> 1);
+            xok[mt] = x < p.X;
+            const uint32_t xq = x / p.x_inner;
+            const uint32_t xr = x - xq * p.x_inner;
+            long long off = (long long)xr * p.sx0;
+            if (p.x_mid != 0xFFFFFFFFu) {
+                const uint32_t x2 = xq / p.x_mid;
+                const uint32_t x1 = xq - x2 * p.x_mid;
+                off += (long long)x2 * p.sx2 + (long long)x1 * p.sx1;
+            } else {
+                off += (long long)xq * p.sx1;
+            }
+            xoff[mt] = off;
+        }
+        const uint32_t wbase = p.w_first + tile_w * (8 * NTC);  // complex columns
+        const bool plain_w = p.w_inner == 1 && p.ndest == 0;
+#pragma unroll
+        for (int ntc = 0; ntc < NTC; ++ntc) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const uint32_t wl = wbase + 8 * ntc + 2 * t + e;
+                if (wl >= p.Wp) continue;  // Wp = number of complex columns in this mode
+                const uint32_t w = dealt_column(wl, p.deal_mul, p.deal_mod);
+                double* col;
+                if (plain_w) {
+                    col = p.out + 2 * ((long long)w * p.sw1);
+                } else {
+                    const uint32_t wq = w / p.w_inner;
+                    const uint32_t wr = w - wq * p.w_inner;
+                    col = (p.ndest ? p.outs[wq] : p.out) + 2 * ((long long)wq * p.sw1 + (long long)wr * p.sw0);
+                }
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt)
+                    if (xok[mt])
+                        *reinterpret_cast<double2*>(col + 2 * xoff[mt]) = make_double2(re[mt][ntc][e], im[mt][ntc][e]);
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // coefficient image: real (K', W') expansion of M laid out in MMA fragment order, per tile group
 //   image[tile][chunk][h][nt][lane][e] = M'[16*chunk + 8h + 2t + e][w_first + 8*NT*tile + 8nt + g]
@@ -398,6 +628,9 @@ struct ImageParams {
     int NT, nchunks, tiles_w, w_first;
     int coulomb;       // 1: M[k, w] = alpha / sqrt((m[k] - m[w])^2 + a^2), m = grid (ODQD interaction)
     double alpha, a2;
+    unsigned deal_mul, deal_mod;  // image column j holds M[:, (j * deal_mul) % deal_mod] (see QuarterParams)
+    int split;         // 1: complex A x real M, image of quarter_gemm_split_kernel (NT holds NTC, Wp complex columns)
+    int K;             // split: complex k extent
 };
 
 __device__ __forceinline__ double image_value(const ImageParams& q, int kp, int wp) {
@@ -410,8 +643,9 @@ __device__ __forceinline__ double image_value(const ImageParams& q, int kp, int 
     const bool out_complex = q.m_complex || q.a_complex;
     const int k = q.a_complex ? (kp >> 1) : kp;
     const int ka = q.a_complex ? (kp & 1) : 0;  // 0: real part of A column, 1: imaginary part
-    const int w = out_complex ? (wp >> 1) : wp;
+    int w = out_complex ? (wp >> 1) : wp;
     const int wb = out_complex ? (wp & 1) : 0;  // 0: real part of output, 1: imaginary part
+    if (q.deal_mul > 1) w = (int)(((unsigned long long)w * q.deal_mul) % q.deal_mod);
     const long long idx = (long long)k * q.sk + (long long)w * q.sw;
     double mr, mi = 0.0;
     if (q.m_complex) {
@@ -424,6 +658,30 @@ __device__ __forceinline__ double image_value(const ImageParams& q, int kp, int 
     // (ar + i ai)(mr + i mi): re = ar mr - ai mi ; im = ar mi + ai mr
     if (ka == 0) return wb == 0 ? mr : mi;
     return wb == 0 ? -mi : mr;
+}
+
+// image[tile][chunk][ntc][lane][h] = M[8 chunk + 4h + t][w_first + 8 NTC tile + 8 ntc + g]   (split variant)
+__global__ void build_split_image_kernel(ImageParams q, double* __restrict__ image) {
+    const long long per_chunk = 64LL * q.NT;
+    const long long total = (long long)q.tiles_w * q.nchunks * per_chunk;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long r = i;
+        const int h = r & 1; r >>= 1;
+        const int lane = r & 31; r >>= 5;
+        const int ntc = r % q.NT; r /= q.NT;
+        const int chunk = r % q.nchunks;
+        const int tw = r / q.nchunks;
+        const int g = lane >> 2, t = lane & 3;
+        const int k = 8 * chunk + 4 * h + t;
+        int w = q.w_first + 8 * q.NT * tw + 8 * ntc + g;
+        double v = 0.0;
+        if (k < q.K && w < q.Wp) {
+            if (q.deal_mul > 1) w = (int)(((unsigned long long)w * q.deal_mul) % q.deal_mod);
+            v = q.m[(long long)k * q.sk + (long long)w * q.sw];
+        }
+        image[i] = v;
+    }
 }
 
 __global__ void build_image_kernel(ImageParams q, double* __restrict__ image) {
@@ -451,12 +709,16 @@ __global__ void build_image_kernel(ImageParams q, double* __restrict__ image) {
 // The W' real columns are cut into 8-wide MMA column tiles; those are dealt to CTA tiles of NT <= 8
 // column tiles each, in at most two groups whose NT differ by one (e.g. W' = 400 -> 6 x NT=7 + 1 x NT=8),
 // so no CTA tile carries more than 7 padding columns.  Each group is one persistent launch.
+// Development switch (QS_DISABLE_SPLIT=1): lower complex A x real M through the generic 4M image instead.
+const bool g_disable_split = getenv("QS_DISABLE_SPLIT") != nullptr;
+
 struct TileGroup {
     int NT, tiles_w, w_first;
     int64_t image_offset;  // doubles
 };
 
 struct Tiling {
+    int split;  // complex A x real M: quarter_gemm_split_kernel, TileGroup::NT holds NTC (complex column tiles)
     int Kp, Wp, nchunks, last_halves, ngroups;
     TileGroup group[2];
     int64_t image_doubles;
@@ -465,23 +727,26 @@ struct Tiling {
 Tiling make_tiling(int64_t K, int64_t W, int a_dtype, int m_dtype) {
     Tiling tl;
     const bool out_complex = a_dtype == QS_C128 || m_dtype == QS_C128;
+    tl.split = (a_dtype == QS_C128 && m_dtype == QS_F64 && !g_disable_split) ? 1 : 0;
     tl.Kp = (int)(K * (a_dtype == QS_C128 ? 2 : 1));
-    tl.Wp = (int)(W * (out_complex ? 2 : 1));
+    tl.Wp = (int)(tl.split ? W : W * (out_complex ? 2 : 1));  // split: complex columns, 8 per column tile
     tl.nchunks = (int)qs_ceil_div(tl.Kp, kChunkK);
     tl.last_halves = (tl.Kp - (tl.nchunks - 1) * kChunkK) <= 8 ? 1 : 2;
+    const int max_nt = tl.split ? 4 : 8;                       // column tiles per CTA tile
+    const int per_tile_chunk = tl.split ? 64 : 128;            // image doubles per column tile and chunk
     const int col_tiles = (int)qs_ceil_div(tl.Wp, 8);
-    const int cta_tiles = (int)qs_ceil_div(col_tiles, 8);
+    const int cta_tiles = (int)qs_ceil_div(col_tiles, max_nt);
     const int base = col_tiles / cta_tiles, extra = col_tiles % cta_tiles;
     tl.ngroups = 0;
     int64_t off = 0;
     int w = 0;
     if (extra > 0) {
         tl.group[tl.ngroups++] = {base + 1, extra, w, off};
-        off += (int64_t)extra * tl.nchunks * 128 * (base + 1);
+        off += (int64_t)extra * tl.nchunks * per_tile_chunk * (base + 1);
         w += extra * (base + 1) * 8;
     }
     tl.group[tl.ngroups++] = {base, cta_tiles - extra, w, off};
-    off += (int64_t)(cta_tiles - extra) * tl.nchunks * 128 * base;
+    off += (int64_t)(cta_tiles - extra) * tl.nchunks * per_tile_chunk * base;
     tl.image_doubles = off;
     return tl;
 }
@@ -535,21 +800,54 @@ int launch_nt(int NT, const CUtensorMap& map, const QuarterParams& p, cudaStream
     return QS_ERR_INVALID;
 }
 
+template <int NTC>
+int launch_split_variant(const CUtensorMap& map, const QuarterParams& p, cudaStream_t st) {
+    constexpr int smem = SplitRing<NTC>::kSmemBytes;
+    static bool configured = false;
+    if (!configured) {
+        QS_CUDA(cudaFuncSetAttribute(quarter_gemm_split_kernel<NTC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    const int64_t total = (int64_t)p.tiles_x * p.tiles_w;
+    const int64_t resident = qs_sm_count();
+    const int64_t grid = total < resident ? total : resident;
+    quarter_gemm_split_kernel<NTC><<<(unsigned)grid, kThreads, smem, st>>>(map, p);
+    QS_LAUNCH_CHECK();
+    return QS_OK;
+}
+
+int launch_split(int NTC, const CUtensorMap& map, const QuarterParams& p, cudaStream_t st) {
+    switch (NTC) {
+        case 1: return launch_split_variant<1>(map, p, st);
+        case 2: return launch_split_variant<2>(map, p, st);
+        case 3: return launch_split_variant<3>(map, p, st);
+        case 4: return launch_split_variant<4>(map, p, st);
+    }
+    qs_set_error("internal: NTC=%d out of range", NTC);
+    return QS_ERR_INVALID;
+}
+
 int build_image(ImageParams q, const Tiling& tl, void* image, void* stream) {
     q.Kp = tl.Kp;
     q.Wp = tl.Wp;
     q.nchunks = tl.nchunks;
+    q.split = tl.split;
+    q.K = tl.Kp / 2;
+    QS_REQUIRE(!(tl.split && q.coulomb), "internal: the Coulomb image has no split form");
     for (int gi = 0; gi < tl.ngroups; ++gi) {
         const TileGroup& gr = tl.group[gi];
         q.NT = gr.NT;
         q.tiles_w = gr.tiles_w;
         q.w_first = gr.w_first;
-        const long long total = (long long)gr.tiles_w * tl.nchunks * 128 * gr.NT;
+        const long long total = (long long)gr.tiles_w * tl.nchunks * (tl.split ? 64 : 128) * gr.NT;
         long long blocks = qs_ceil_div(total, 256);
         const long long cap = (long long)qs_sm_count() * 16;
         if (blocks > cap) blocks = cap;
-        build_image_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-            q, static_cast<double*>(image) + gr.image_offset);
+        double* dst = static_cast<double*>(image) + gr.image_offset;
+        if (tl.split)
+            build_split_image_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(q, dst);
+        else
+            build_image_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(q, dst);
         QS_LAUNCH_CHECK();
     }
     return QS_OK;
@@ -565,9 +863,36 @@ extern "C" int qs_coeff_image_bytes(int64_t K, int64_t W, int a_dtype, int m_dty
     return QS_OK;
 }
 
-extern "C" int qs_build_coeff_image(const void* m, int m_dtype, int64_t m_sk, int64_t m_sw, int m_conj, int64_t K,
-                                    int64_t W, int a_dtype, void* image, void* stream) {
+namespace {
+int64_t gcd64(int64_t a, int64_t b) {
+    while (b) {
+        const int64_t t = a % b;
+        a = b;
+        b = t;
+    }
+    return a;
+}
+}  // namespace
+
+// Multiplier of the column dealing for W output columns: the integer nearest to W / golden ratio that is
+// coprime to W (consecutive multiples are then a low-discrepancy sequence mod W).  1 = no dealing.
+extern "C" int qs_scatter_deal(int64_t W, int64_t* w_deal) {
+    QS_REQUIRE(W > 0 && w_deal, "qs_scatter_deal: bad arguments");
+    *w_deal = 1;
+    if (W < 16) return QS_OK;
+    int64_t s = (int64_t)((double)W * 0.6180339887498949 + 0.5);
+    while (s < W && gcd64(s, W) != 1) ++s;
+    if (s > 1 && s < W) *w_deal = s;
+    return QS_OK;
+}
+
+extern "C" int qs_build_coeff_image_dealt(const void* m, int m_dtype, int64_t m_sk, int64_t m_sw, int m_conj,
+                                          int64_t K, int64_t W, int a_dtype, int64_t w_deal, void* image,
+                                          void* stream) {
     QS_REQUIRE(m && image && K > 0 && W > 0, "qs_build_coeff_image: bad arguments");
+    QS_REQUIRE(w_deal >= 1 && w_deal < (W > 1 ? W : 2) && gcd64(w_deal, W) == 1,
+               "qs_build_coeff_image: the dealing multiplier %lld is not coprime to W = %lld", (long long)w_deal,
+               (long long)W);
     const Tiling tl = make_tiling(K, W, a_dtype, m_dtype);
     ImageParams q;
     memset(&q, 0, sizeof(q));
@@ -577,7 +902,14 @@ extern "C" int qs_build_coeff_image(const void* m, int m_dtype, int64_t m_sk, in
     q.m_complex = m_dtype == QS_C128;
     q.a_complex = a_dtype == QS_C128;
     q.conj = m_conj;
+    q.deal_mul = (unsigned)w_deal;
+    q.deal_mod = (unsigned)W;
     return build_image(q, tl, image, stream);
+}
+
+extern "C" int qs_build_coeff_image(const void* m, int m_dtype, int64_t m_sk, int64_t m_sw, int m_conj, int64_t K,
+                                    int64_t W, int a_dtype, void* image, void* stream) {
+    return qs_build_coeff_image_dealt(m, m_dtype, m_sk, m_sw, m_conj, K, W, a_dtype, 1, image, stream);
 }
 
 // Coefficient image of the shielded-Coulomb matrix W[p, q] on `grid` (real, Gp x Gp), never
@@ -598,8 +930,12 @@ namespace {
 
 int quarter_launch(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda, const void* image, int m_dtype,
                    int64_t W, void* out, void* const* out_table, int64_t n_dest, int64_t x_inner, int64_t x_mid,
-                   int64_t sx0, int64_t sx1, int64_t sx2, int64_t w_inner, int64_t sw0, int64_t sw1, void* stream) {
+                   int64_t sx0, int64_t sx1, int64_t sx2, int64_t w_inner, int64_t sw0, int64_t sw1, int64_t w_deal,
+                   void* stream) {
     QS_REQUIRE(A && image && (out || out_table), "qs_quarter_transform: null pointer");
+    QS_REQUIRE(w_deal >= 1 && w_deal < (W > 1 ? W : 2) && gcd64(w_deal, W) == 1,
+               "qs_quarter_transform_scatter: the dealing multiplier %lld is not coprime to W = %lld",
+               (long long)w_deal, (long long)W);
     QS_REQUIRE(X > 0 && K > 0 && W > 0 && lda >= K, "qs_quarter_transform: bad extents");
     QS_REQUIRE(X < (1LL << 31) - kBlockX, "qs_quarter_transform: X=%lld exceeds 2^31", (long long)X);
     QS_REQUIRE(x_inner > 0 && w_inner > 0 && x_inner < (1LL << 32) && w_inner < (1LL << 31) && x_mid > 0 &&
@@ -646,6 +982,7 @@ int quarter_launch(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda
 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int span = -1;
+    // issued flops; the split variant's Wp counts complex columns, each fed by Kp real multiply-adds per row
     qs_timing_begin(QS_FAMILY_QUARTER_GEMM, 2.0 * (double)X * tl.Kp * tl.Wp, stream, &span);
     for (int gi = 0; gi < tl.ngroups; ++gi) {
         const TileGroup& gr = tl.group[gi];
@@ -671,8 +1008,12 @@ int quarter_launch(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda
         p.sw0 = sw0;
         p.sw1 = n_dest ? 0 : sw1;
         p.vec2 = vec2;
+        p.deal_mul = (uint32_t)w_deal;
+        p.deal_mod = (uint32_t)W;
         QS_REQUIRE((int64_t)p.tiles_x * p.tiles_w < (1LL << 31), "qs_quarter_transform: too many tiles");
-        const int rc = out_complex ? launch_nt<true>(gr.NT, map, p, st) : launch_nt<false>(gr.NT, map, p, st);
+        const int rc = tl.split      ? launch_split(gr.NT, map, p, st)
+                       : out_complex ? launch_nt<true>(gr.NT, map, p, st)
+                                     : launch_nt<false>(gr.NT, map, p, st);
         if (rc) return rc;
     }
     qs_timing_end(span, stream);
@@ -685,14 +1026,15 @@ extern "C" int qs_quarter_transform(const void* A, int a_dtype, int64_t X, int64
                                     int m_dtype, int64_t W, void* out, int64_t x_inner, int64_t sx0, int64_t sx1,
                                     int64_t w_inner, int64_t sw0, int64_t sw1, void* stream) {
     return quarter_launch(A, a_dtype, X, K, lda, image, m_dtype, W, out, nullptr, 0, x_inner, 0xFFFFFFFFLL, sx0, sx1, 0,
-                          w_inner, sw0, sw1, stream);
+                          w_inner, sw0, sw1, 1, stream);
 }
 
 extern "C" int qs_quarter_transform_scatter(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda,
                                             const void* image, int m_dtype, int64_t W, void* const* host_out_table,
                                             int64_t n_dest, int64_t x_inner, int64_t x_mid, int64_t sx0, int64_t sx1,
-                                            int64_t sx2, int64_t w_inner, int64_t sw0, void* stream) {
+                                            int64_t sx2, int64_t w_inner, int64_t sw0, int64_t w_deal,
+                                            void* stream) {
     QS_REQUIRE(host_out_table && n_dest > 0, "qs_quarter_transform_scatter: empty destination table");
     return quarter_launch(A, a_dtype, X, K, lda, image, m_dtype, W, nullptr, host_out_table, n_dest, x_inner, x_mid, sx0,
-                          sx1, sx2, w_inner, sw0, 0, stream);
+                          sx1, sx2, w_inner, sw0, 0, w_deal, stream);
 }

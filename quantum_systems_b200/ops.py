@@ -66,10 +66,24 @@ def _coefficients(C, C_tilde):
     return C, C_tilde
 
 
+def real_coefficients_if_exact(u, C, C_tilde):
+    """Complex ``u`` with coefficients of complex dtype whose imaginary parts are all exactly zero (the usual
+    case downstream: every array of a ``GeneralOrbitalSystem`` is complex128, basis_set.py:632-634, while
+    Hartree-Fock coefficients of a real Hamiltonian are real-valued): hand the kernels the real parts, which
+    selects the split "2M" quarter GEMM -- half the tensor-core work of the 4M product, same result (the
+    skipped products are exact zeros).  Only when ``u`` is complex, so the result dtype does not change."""
+    if not (u.is_complex() and C.is_complex()):
+        return C, C_tilde
+    if bool(torch.any(C.imag != 0)) or (C_tilde is not None and bool(torch.any(C_tilde.imag != 0))):
+        return C, C_tilde
+    return C.real.contiguous(), (C_tilde.real.contiguous() if C_tilde is not None else None)
+
+
 def transform_two_body(u, C, C_tilde=None):
     """``u'_pqrs = sum C~[p,a] C~[q,b] u[a,b,c,d] C[c,r] C[d,s]`` (reference basis_set.py:336-350)."""
     u = _device_tensor(u, "u")
     C, C_tilde = _coefficients(C, C_tilde)
+    C, C_tilde = real_coefficients_if_exact(u, C, C_tilde)
     n, m = C.shape
     if tuple(u.shape) != (n, n, n, n):
         raise ValueError(f"u must have shape {(n,) * 4} to be contracted with C {tuple(C.shape)}, got {tuple(u.shape)}")
@@ -103,16 +117,25 @@ def transform_one_body(h, C, C_tilde=None):
     return out
 
 
-def coeff_image(M, K, W, a_dtype, stride_k, stride_w, conj=False):
-    """Fragment-ordered image of ``M[k, w] = M.flat[k*stride_k + w*stride_w]`` for quarter_transform."""
+def scatter_deal(W):
+    """Multiplier of the column dealing of a scattering quarter transform with ``W`` output columns
+    (``qs_scatter_deal``): column j of the tile order is physical column ``(j * deal) % W``."""
+    deal = ctypes.c_int64(1)
+    _native.call("qs_scatter_deal", int(W), ctypes.byref(deal))
+    return deal.value
+
+
+def coeff_image(M, K, W, a_dtype, stride_k, stride_w, conj=False, deal=1):
+    """Fragment-ordered image of ``M[k, w] = M.flat[k*stride_k + w*stride_w]`` for quarter_transform
+    (``deal`` > 1: columns dealt for a scattering launch, see ``scatter_deal``)."""
     M = _device_tensor(M, "M")
     a_code = _DTYPES[a_dtype]
     nbytes = ctypes.c_int64(0)
     _native.call("qs_coeff_image_bytes", K, W, a_code, _code(M), ctypes.byref(nbytes))
     image = torch.empty(nbytes.value // 8, dtype=torch.float64, device=M.device)
     _native.call(
-        "qs_build_coeff_image", _ptr(M), _code(M), stride_k, stride_w, int(bool(conj)), K, W, a_code, _ptr(image),
-        _stream(),
+        "qs_build_coeff_image_dealt", _ptr(M), _code(M), stride_k, stride_w, int(bool(conj)), K, W, a_code, int(deal),
+        _ptr(image), _stream(),
     )
     return image
 

@@ -100,10 +100,15 @@ class CudaEngine:
 
         return _arrays.to_device(a, dtype)
 
-    def image(self, M, K, W, a_dtype, stride_k, stride_w, conj=False):
+    def scatter_deal(self, W):
         from . import ops
 
-        return ops.coeff_image(M, K, W, a_dtype, stride_k, stride_w, conj=conj)
+        return ops.scatter_deal(W)
+
+    def image(self, M, K, W, a_dtype, stride_k, stride_w, conj=False, deal=1):
+        from . import ops
+
+        return ops.coeff_image(M, K, W, a_dtype, stride_k, stride_w, conj=conj, deal=deal)
 
     def pad_rows(self, src, rows, n, pitch, dst):
         _native.call(
@@ -148,14 +153,15 @@ class CudaEngine:
         )
         return out
 
-    def quarter_scatter(self, A, X, K, lda, image, m_dtype, W, dests, x_inner, x_mid, sx0, sx1, sx2, w_inner, sw0):
+    def quarter_scatter(self, A, X, K, lda, image, m_dtype, W, dests, x_inner, x_mid, sx0, sx1, sx2, w_inner, sw0,
+                        deal=1):
         if X <= 0:
             return
         table = (ctypes.c_void_p * len(dests))(*[buf.at(off) for buf, off in dests])
         _native.call(
             "qs_quarter_transform_scatter", ctypes.c_void_p(A.at(0)), _CODES[A.dtype], X, K, lda,
             ctypes.c_void_p(image.data_ptr()), _CODES[m_dtype], W, table, len(dests), x_inner, max(x_mid, 1), sx0, sx1,
-            sx2, w_inner, sw0, self._stream(),
+            sx2, w_inner, sw0, int(deal), self._stream(),
         )
 
 
@@ -452,6 +458,17 @@ class _RankTransform:
             self.img3 = eng.image(C_tilde, n, m, self.t_dtype, 1, n)
         else:
             self.img3 = eng.image(C, n, m, self.t_dtype, m, 1, conj=True)  # C~ = C^dagger, basis_set.py:338-339
+        # The scattering steps deal their output columns over all destinations (uniform NVLink traffic): their
+        # images hold the columns of C / C~ in dealt order.
+        self.deal = eng.scatter_deal(m) if self.ctx.exchange == "peer" and self.ctx.world > 1 else 1
+        if self.deal > 1:
+            self.img2_scatter = eng.image(C, n, m, self.t_dtype, m, 1, deal=self.deal)
+            if C_tilde is not None:
+                self.img4_scatter = eng.image(C_tilde, n, m, self.t_dtype, 1, n, deal=self.deal)
+            else:
+                self.img4_scatter = eng.image(C, n, m, self.t_dtype, m, 1, conj=True, deal=self.deal)
+        else:
+            self.img2_scatter, self.img4_scatter = self.img2, self.img3
         self.scratch = eng.empty(self.scratch_numel(), self.t_dtype)
 
     def step1(self, u_in):
@@ -472,8 +489,8 @@ class _RankTransform:
         eng, n, m, A, P = self.engine, self.n, self.m, self.A, self.P
         a0 = self.a_off[self.rank]
         dests = [(recv[j], a0 * P) for j in range(self.ctx.world)]
-        eng.quarter_scatter(self.scratch, m * A * n, n, P, self.img2, self.c_dtype, m, dests, n, A, 1, P, n * P,
-                            self.r_block, m * n * P)
+        eng.quarter_scatter(self.scratch, m * A * n, n, P, self.img2_scatter, self.c_dtype, m, dests, n, A, 1, P, n * P,
+                            self.r_block, m * n * P, deal=self.deal)
 
     def step2_local(self, send):
         """Collective schedule: T2[r, s, a_loc, b] written locally, blocks of r contiguous per destination."""
@@ -505,8 +522,8 @@ class _RankTransform:
         eng, n, m, R, P = self.engine, self.n, self.m, self.R, self.P
         r0 = self.r_off[self.rank]
         dests = [(out[j], r0 * m) for j in range(self.ctx.world)]
-        eng.quarter_scatter(self.scratch, m * R * m, n, P, self.img3, self.c_dtype, m, dests, m, R, 1, m, m * m,
-                            self.r_block, m**3)
+        eng.quarter_scatter(self.scratch, m * R * m, n, P, self.img4_scatter, self.c_dtype, m, dests, m, R, 1, m, m * m,
+                            self.r_block, m**3, deal=self.deal)
 
     def step4_local(self, out_local):
         """Collective schedule: u'[p, q, r_loc, s] dense on this rank (sharded on the third index)."""
@@ -659,6 +676,9 @@ class ShardedBasisSet:
         if C_tilde is not None:
             dt = torch.complex128 if torch.complex128 in (C.dtype, C_tilde.dtype) else torch.float64
             C, C_tilde = C.to(dt), C_tilde.to(dt)
+        if self.u.dtype == torch.complex128:
+            # real-valued coefficients of complex dtype select the split (2M) quarter GEMM, see ops
+            C, C_tilde = ops.real_coefficients_if_exact(self.h.to(torch.complex128), C, C_tilde)
         self.l = C.shape[1]
         self.h = ops.transform_one_body(self.h, C, C_tilde)
         if self.s is not None:

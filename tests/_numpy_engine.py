@@ -33,10 +33,21 @@ class NumpyEngine:
         t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
         return t if dtype is None else t.to(dtype)
 
-    def image(self, M, K, W, a_dtype, stride_k, stride_w, conj=False):
+    def scatter_deal(self, W):
+        """Same rule as qs_scatter_deal (include/qsb200.h): nearest integer to W / golden ratio coprime to W."""
+        from math import gcd
+
+        if W < 16:
+            return 1
+        s = int(W * 0.6180339887498949 + 0.5)
+        while s < W and gcd(s, W) != 1:
+            s += 1
+        return s if 1 < s < W else 1
+
+    def image(self, M, K, W, a_dtype, stride_k, stride_w, conj=False, deal=1):
         flat = (M.numpy() if isinstance(M, torch.Tensor) else np.asarray(M)).reshape(-1)
         k = np.arange(K)[:, None] * stride_k
-        w = np.arange(W)[None, :] * stride_w
+        w = ((np.arange(W) * deal) % W)[None, :] * stride_w  # image column j holds M[:, (j * deal) % W]
         dense = flat[k + w]
         return dense.conj() if conj else dense
 
@@ -60,10 +71,15 @@ class NumpyEngine:
         aw = (w // w_inner) * sw1 + (w % w_inner) * sw0
         out.flat()[out_offset + ax[:, None] + aw[None, :]] = res
 
-    def quarter_scatter(self, A, X, K, lda, image, m_dtype, W, dests, x_inner, x_mid, sx0, sx1, sx2, w_inner, sw0):
+    def quarter_scatter(self, A, X, K, lda, image, m_dtype, W, dests, x_inner, x_mid, sx0, sx1, sx2, w_inner, sw0,
+                        deal=1):
         if X <= 0:
             return
         res = self._product(A, X, K, lda, image)
+        if deal > 1:  # column j of the product is physical column (j * deal) % W
+            physical = np.empty_like(res)
+            physical[:, (np.arange(W) * deal) % W] = res
+            res = physical
         x = np.arange(X)
         x_mid = max(x_mid, 1)
         xq = x // x_inner

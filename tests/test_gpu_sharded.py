@@ -36,6 +36,8 @@ def dev(x):
     (20, 12, True, True, True),
     (12, 12, False, True, False),
     (40, 40, False, False, False),
+    (24, 24, True, False, False),   # complex u, real C: the split (2M) quarter GEMM, scattering and local
+    (14, 18, True, False, True),
 ])
 def test_emulated_sharded_transform(world, n, m, u_complex, c_complex, biorth):
     from quantum_systems_b200 import sharded

@@ -22,6 +22,28 @@ def rand(rng, shape, complex_):
     return x + 1j * rng.standard_normal(shape) if complex_ else x
 
 
+def test_scatter_deal_rule_is_a_permutation():
+    """The numpy stand-in and the library agree on the dealing multiplier, and it permutes the columns."""
+    import ctypes
+    from math import gcd
+
+    from quantum_systems_b200 import _native
+    from quantum_systems_b200.build import build
+
+    build()
+    lib = _native.load()
+    for W in list(range(1, 70)) + [128, 148, 192, 256, 400, 401]:
+        deal = ctypes.c_int64(0)
+        assert lib.qs_scatter_deal(W, ctypes.byref(deal)) == 0
+        assert deal.value == NumpyEngine().scatter_deal(W)
+        assert 1 <= deal.value < max(W, 2) and gcd(deal.value, W) == 1
+        assert sorted((j * deal.value) % W for j in range(W)) == list(range(W))
+        if W >= 64:  # any 32 consecutive logical columns touch every eighth of the range
+            for start in (0, W // 3):
+                hit = {((j * deal.value) % W) * 8 // W for j in range(start, start + 32)}
+                assert hit == set(range(8))
+
+
 def test_block_partition():
     from quantum_systems_b200.sharded import block_partition
 
@@ -41,6 +63,9 @@ def test_block_partition():
     (7, 10, False, False, False),  # rectangular, grows
     (10, 6, True, True, True),     # rectangular, shrinks, bi-orthogonal complex
     (6, 6, False, True, False),    # real u, complex C
+    (8, 8, True, False, False),    # complex u, real C
+    (12, 17, False, False, False),  # >= 16 new columns: the scattering steps deal their columns (qs_scatter_deal)
+    (16, 16, True, True, True),
 ])
 def test_emulated_peer_schedule_matches_oracle(world, n, m, u_complex, c_complex, biorth):
     from quantum_systems_b200 import sharded

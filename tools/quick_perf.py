@@ -29,6 +29,18 @@ def main():
         print(json.dumps({"op": "transform_two_body", "n": n, "complex": cplx, "ms": round(ms, 3),
                           "tflops": round(flops / ms * 1e-9, 2), "frac_of_dmma_peak": round(flops / ms * 1e-9 / peak, 3)}))
         del u
+    # complex u with REAL coefficients: the split (2M) quarter GEMM; 16 n^5 real flops are necessary
+    # (QS_DISABLE_SPLIT=1 in the environment lowers it through the generic 4M image for comparison)
+    for n in (40, 96, 128):
+        u = torch.randn((n,) * 4, dtype=torch.complex128, device="cuda")
+        C = torch.linalg.qr(torch.randn((n, n), dtype=torch.float64, device="cuda"))[0].contiguous()
+        for label, coeff in (("real C", C), ("complex-typed real C", C.to(torch.complex128))):
+            ms = timed(lambda: ops.transform_two_body(u, coeff))
+            print(json.dumps({"op": "transform_two_body", "n": n, "u": "complex128", "C": label, "ms": round(ms, 3),
+                              "tflops_2M": round(16.0 * n**5 / ms * 1e-9, 2),
+                              "frac_of_dmma_peak_2M": round(16.0 * n**5 / ms * 1e-9 / peak, 3),
+                              "split_disabled": bool(os.environ.get("QS_DISABLE_SPLIT"))}))
+        del u
     for l in [64, 100]:
         u = torch.randn((l,) * 4, dtype=torch.float64, device="cuda")
         for od in (torch.float64, torch.complex128):
