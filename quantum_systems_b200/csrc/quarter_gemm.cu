@@ -409,7 +409,8 @@ quarter_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 template <int NTC>
 struct SplitRing {
     static constexpr int kBTileBytes = NTC * 512;  // 8 complex k x 8*NTC columns, one double each
-    static constexpr int kStageBytes = kATileBytes + kBTileBytes;
+    // stages stay 1 KiB aligned: the 128-byte TMA swizzle of the A tile is a function of the address bits
+    static constexpr int kStageBytes = kATileBytes + ((kBTileBytes + 1023) / 1024) * 1024;
     static constexpr int kFit = (110 * 1024) / kStageBytes;
     static constexpr int kStages = kFit < 6 ? kFit : 6;
     static constexpr int kRingBytes = kStages * kStageBytes;
@@ -466,7 +467,7 @@ quarter_gemm_split_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                     const uint32_t s = j % kStages;
                     if (j >= (uint32_t)kStages) mbar_wait(bar_empty + 8 * s, ((j / kStages) - 1) & 1);
                     const uint32_t full = bar_full + 8 * s;
-                    mbar_expect_tx(full, kStageBytes);
+                    mbar_expect_tx(full, kATileBytes + kBTileBytes);
                     const uint32_t dst = ring + s * kStageBytes;
                     tma_load_2d(dst, &map_a, c * kChunkK, px0, full);
                     bulk_load_1d(dst + kATileBytes, img + (size_t)c * (kBTileBytes / 8), kBTileBytes, full);
