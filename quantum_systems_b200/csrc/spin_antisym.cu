@@ -259,9 +259,10 @@ __global__ void __launch_bounds__(256) spin2_tb_kernel(const double2* __restrict
 
 extern "C" int qs_add_spin_two_body(const void* u, int in_dtype, int64_t l, void* out, int out_dtype, int anti_symmetrize,
                                     int64_t p_begin, int64_t p_end, void* stream) {
-    QS_REQUIRE(u && out && l > 0, "qs_add_spin_two_body: bad arguments");
+    QS_REQUIRE(l > 0 && 0 <= p_begin && p_begin <= p_end && p_end <= 2 * l, "qs_add_spin_two_body: bad plane range");
     QS_REQUIRE(!(in_dtype == QS_C128 && out_dtype == QS_F64), "qs_add_spin_two_body: cannot narrow complex to real");
-    QS_REQUIRE(0 <= p_begin && p_begin <= p_end && p_end <= 2 * l, "qs_add_spin_two_body: bad plane range");
+    if (p_begin == p_end) return QS_OK;  // an empty shard (trailing rank of a block partition)
+    QS_REQUIRE(u && out, "qs_add_spin_two_body: bad arguments");
     QS_REQUIRE(l <= 32767, "qs_add_spin_two_body: l too large");
     if (p_begin == p_end) return QS_OK;
     const int tiles = (int)qs_ceil_div(l, kTile);
@@ -307,8 +308,9 @@ extern "C" int qs_add_spin_two_body(const void* u, int in_dtype, int64_t l, void
 
 extern "C" int qs_anti_symmetrize(const void* u, int dtype, int64_t n, void* out, int64_t p_begin, int64_t p_end,
                                   void* stream) {
-    QS_REQUIRE(u && out && n > 0 && u != out, "qs_anti_symmetrize: bad arguments (in-place is not supported)");
-    QS_REQUIRE(0 <= p_begin && p_begin <= p_end && p_end <= n, "qs_anti_symmetrize: bad plane range");
+    QS_REQUIRE(n > 0 && 0 <= p_begin && p_begin <= p_end && p_end <= n, "qs_anti_symmetrize: bad plane range");
+    if (p_begin == p_end) return QS_OK;  // an empty shard
+    QS_REQUIRE(u && out && u != out, "qs_anti_symmetrize: bad arguments (in-place is not supported)");
     QS_REQUIRE(n <= 65535, "qs_anti_symmetrize: n too large");
     if (p_begin == p_end) return QS_OK;
     const int tiles = (int)qs_ceil_div(n, kTile);
@@ -350,8 +352,9 @@ extern "C" int qs_add_spin_one_body(const void* h, int in_dtype, int64_t l, void
 
 extern "C" int qs_spin_squared_two_body(const void* sx, const void* sy, const void* sz, int64_t n, int anti_symmetrize,
                                         void* out, int64_t p_begin, int64_t p_end, void* stream) {
-    QS_REQUIRE(sx && sy && sz && out && n > 0, "qs_spin_squared_two_body: bad arguments");
-    QS_REQUIRE(0 <= p_begin && p_begin <= p_end && p_end <= n, "qs_spin_squared_two_body: bad plane range");
+    QS_REQUIRE(n > 0 && 0 <= p_begin && p_begin <= p_end && p_end <= n, "qs_spin_squared_two_body: bad plane range");
+    if (p_begin == p_end) return QS_OK;  // an empty shard
+    QS_REQUIRE(sx && sy && sz && out, "qs_spin_squared_two_body: bad arguments");
     if (p_begin == p_end) return QS_OK;
     const int smem = 6 * (int)n * 16;
     QS_REQUIRE(smem <= 200 * 1024, "qs_spin_squared_two_body: n too large");

@@ -30,7 +30,7 @@ def main():
     ops.transform_one_body(h, Cc)
 
     # spin doubling fused with anti-symmetrisation (+ cast), stand-alone anti-symmetrisation, one-body kron
-    l = 64
+    l = 48
     us = torch.randn((l,) * 4, dtype=f64, device="cuda")
     a = ops.add_spin_two_body(us, anti_symmetrize=True, out_dtype=f64)
     ops.add_spin_two_body(us, anti_symmetrize=True, out_dtype=c128)
@@ -40,7 +40,7 @@ def main():
     ops.spin_squared_two_body(sx[0], sx[1], sx[2], anti_symmetrize=True)
 
     # Fock matrices, reference-energy traces, o/v block extraction, scaled sums
-    n, n_occ = 128, 10
+    n, n_occ = 96, 10
     hr = torch.randn((n, n), dtype=f64, device="cuda")
     ops.fock_general(hr, a, n_occ)
     ops.fock_spatial(hr, a, n_occ)
@@ -51,7 +51,7 @@ def main():
     ops.scale_add(a, 0.5, a, 2.0)
 
     # grid builders: ODQD shielded Coulomb (config 3 shape, reduced), 2-D oscillator elements, sinc-DVR transform
-    G, lq = 1001, 64
+    G, lq = 1001, 48
     Cg = torch.randn((G - 2, lq), dtype=f64, device="cuda")
     grid = torch.linspace(-10, 10, G, dtype=f64, device="cuda")[1:-1].contiguous()
     ops.odqd_coulomb(Cg, grid, 1.0, 0.25)
