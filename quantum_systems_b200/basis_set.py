@@ -19,7 +19,7 @@ import warnings
 
 import torch
 
-from . import _arrays, ops
+from . import _arrays, ops, streamed
 
 
 def _is_complex(a):
@@ -303,8 +303,12 @@ class BasisSet:
 
     @staticmethod
     def transform_two_body_elements(u, C, np, C_tilde=None):
-        """Four-index transform (basis_set.py:336-350) on the FP64 tensor cores."""
-        out = ops.transform_two_body(_arrays.to_device(u), _arrays.to_device(C), _arrays.to_device(C_tilde))
+        """Four-index transform (basis_set.py:336-350) on the FP64 tensor cores.  A large host-resident ``u``
+        (``np = numpy``) takes the streamed schedule that hides the PCIe copies behind the kernels."""
+        C_dev, C_tilde_dev = _arrays.to_device(C), _arrays.to_device(C_tilde)
+        if _arrays.is_host_module(np) and streamed.applicable(u, C_dev):
+            return streamed.transform_two_body(u, C_dev, C_tilde_dev)
+        out = ops.transform_two_body(_arrays.to_device(u), C_dev, C_tilde_dev)
         return _arrays.to_module(out, np)
 
     def get_transformed_h(self, C):
