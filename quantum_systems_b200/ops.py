@@ -66,13 +66,13 @@ def _coefficients(C, C_tilde):
     return C, C_tilde
 
 
-def real_coefficients_if_exact(u, C, C_tilde):
+def real_coefficients_if_exact(u_is_complex, C, C_tilde):
     """Complex ``u`` with coefficients of complex dtype whose imaginary parts are all exactly zero (the usual
     case downstream: every array of a ``GeneralOrbitalSystem`` is complex128, basis_set.py:632-634, while
     Hartree-Fock coefficients of a real Hamiltonian are real-valued): hand the kernels the real parts, which
     selects the split "2M" quarter GEMM -- half the tensor-core work of the 4M product, same result (the
     skipped products are exact zeros).  Only when ``u`` is complex, so the result dtype does not change."""
-    if not (u.is_complex() and C.is_complex()):
+    if not (u_is_complex and C.is_complex()):
         return C, C_tilde
     if bool(torch.any(C.imag != 0)) or (C_tilde is not None and bool(torch.any(C_tilde.imag != 0))):
         return C, C_tilde
@@ -83,7 +83,7 @@ def transform_two_body(u, C, C_tilde=None):
     """``u'_pqrs = sum C~[p,a] C~[q,b] u[a,b,c,d] C[c,r] C[d,s]`` (reference basis_set.py:336-350)."""
     u = _device_tensor(u, "u")
     C, C_tilde = _coefficients(C, C_tilde)
-    C, C_tilde = real_coefficients_if_exact(u, C, C_tilde)
+    C, C_tilde = real_coefficients_if_exact(u.is_complex(), C, C_tilde)
     n, m = C.shape
     if tuple(u.shape) != (n, n, n, n):
         raise ValueError(f"u must have shape {(n,) * 4} to be contracted with C {tuple(C.shape)}, got {tuple(u.shape)}")

@@ -359,7 +359,8 @@ class ShardedTwoBody:
         blocks of the solvers.  Each rank cuts its own planes out of its shard (``qs_extract_block``);
         the pieces are all-gathered (the only communication: the block itself)."""
         ctx = self.ctx
-        (a0, a1), rest = self._bounds(a, b, c, d)[0], self._bounds(a, b, c, d)[1:]
+        (a0, a1), *rest = self._bounds(a, b, c, d)
+        rest = tuple(rest)
         pieces = {}
         for r in ctx.local_ranks:
             p0, p1 = self.planes(r)
@@ -676,9 +677,8 @@ class ShardedBasisSet:
         if C_tilde is not None:
             dt = torch.complex128 if torch.complex128 in (C.dtype, C_tilde.dtype) else torch.float64
             C, C_tilde = C.to(dt), C_tilde.to(dt)
-        if self.u.dtype == torch.complex128:
-            # real-valued coefficients of complex dtype select the split (2M) quarter GEMM, see ops
-            C, C_tilde = ops.real_coefficients_if_exact(self.h.to(torch.complex128), C, C_tilde)
+        # real-valued coefficients of complex dtype select the split (2M) quarter GEMM, see ops
+        C, C_tilde = ops.real_coefficients_if_exact(self.u.dtype == torch.complex128, C, C_tilde)
         self.l = C.shape[1]
         self.h = ops.transform_one_body(self.h, C, C_tilde)
         if self.s is not None:

@@ -57,8 +57,7 @@ def transform_two_body(u_host, C, C_tilde=None):
         raise ValueError(f"u must have shape {(n,) * 4} to be contracted with C {tuple(C.shape)}, got {u_host.shape}")
     device = C.device
     u_dtype = torch.complex128 if u_host.dtype == _numpy.complex128 else torch.float64
-    if u_dtype == torch.complex128:
-        C, C_tilde = ops.real_coefficients_if_exact(torch.empty(0, dtype=u_dtype, device=device), C, C_tilde)
+    C, C_tilde = ops.real_coefficients_if_exact(u_dtype == torch.complex128, C, C_tilde)
     t_dtype = torch.complex128 if torch.complex128 in (u_dtype, C.dtype) else torch.float64
     c_dtype = C.dtype
 
