@@ -197,6 +197,11 @@ int qs_odqd_coulomb_workspace_bytes(int64_t l, int64_t Gp, int64_t* bytes);
 int qs_odqd_coulomb(const double* Cmat, const double* grid, double alpha, double a, int64_t l,
                     int64_t Gp, double* u_out, void* workspace, int64_t workspace_bytes,
                     void* stream);
+/* The same build restricted to planes a in [a_begin, a_end) of u (u_out points at plane a_begin): the
+ * multi-GPU partition of SURVEY.md section 8e -- C and the grid replicated, no communication. */
+int qs_odqd_coulomb_planes(const double* Cmat, const double* grid, double alpha, double a, int64_t l,
+                           int64_t Gp, double* u_out, int64_t a_begin, int64_t a_end, void* workspace,
+                           int64_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Two-dimensional harmonic-oscillator Coulomb elements (Anisimovas & Matulis 1998)

@@ -52,6 +52,7 @@ SIGNATURES = {
     "qs_fock_spatial": [_ptr, _int, _ptr, _int, _i64, _i64, _ptr, _i64, _i64, _ptr],
     "qs_odqd_coulomb_workspace_bytes": [_i64, _i64, ctypes.POINTER(_i64)],
     "qs_odqd_coulomb": [_ptr, _ptr, _dbl, _dbl, _i64, _i64, _ptr, _ptr, _i64, _ptr],
+    "qs_odqd_coulomb_planes": [_ptr, _ptr, _dbl, _dbl, _i64, _i64, _ptr, _i64, _i64, _ptr, _i64, _ptr],
     "qs_tdho_coulomb_workspace_bytes": [ctypes.POINTER(_i64), ctypes.POINTER(_i64), _i64, ctypes.POINTER(_i64)],
     "qs_tdho_coulomb": [ctypes.POINTER(_i64), ctypes.POINTER(_i64), _i64, _dbl, _ptr, _i64, _i64, _ptr, _i64, _ptr],
     "qs_extract_block": [_ptr, _int, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr],

@@ -5,6 +5,10 @@
 //   D[(a,c), p] = C[p,a] C[p,c]                      (Khatri-Rao rows, memory-bound kernel below)
 //   Tt[q, (a,c)] = sum_p D[(a,c), p] W[p, q]         (quarter GEMM, plain rotated store; W image generated from the grid)
 //   u[a,b,c,d]  = sum_q D[(b,d), q] Tt[q, (a,c)]     (quarter GEMM; the acbd -> abcd permutation is the store stride)
+//
+// Multi-GPU: the build shards on the leading index a.  A rank computes only the rows
+// (a_loc, c) of T and the planes u[a_begin:a_end] -- C and the grid are replicated, D is built whole (it is the
+// A operand of the second GEMM for every (b, d)), and there is no communication.
 #include "common.cuh"
 
 namespace {
@@ -59,8 +63,16 @@ extern "C" int qs_odqd_coulomb_workspace_bytes(int64_t l, int64_t Gp, int64_t* b
 
 extern "C" int qs_odqd_coulomb(const double* Cmat, const double* grid, double alpha, double a, int64_t l, int64_t Gp,
                                double* u_out, void* workspace, int64_t workspace_bytes, void* stream) {
-    QS_REQUIRE(Cmat && grid && u_out && workspace, "qs_odqd_coulomb: null pointer");
+    return qs_odqd_coulomb_planes(Cmat, grid, alpha, a, l, Gp, u_out, 0, l, workspace, workspace_bytes, stream);
+}
+
+extern "C" int qs_odqd_coulomb_planes(const double* Cmat, const double* grid, double alpha, double a, int64_t l,
+                                      int64_t Gp, double* u_out, int64_t a_begin, int64_t a_end, void* workspace,
+                                      int64_t workspace_bytes, void* stream) {
     QS_REQUIRE(l > 0 && Gp > 0 && l <= 4096, "qs_odqd_coulomb: bad extents");
+    QS_REQUIRE(0 <= a_begin && a_begin <= a_end && a_end <= l, "qs_odqd_coulomb: bad plane range");
+    if (a_begin == a_end) return QS_OK;  // an empty shard
+    QS_REQUIRE(Cmat && grid && u_out && workspace, "qs_odqd_coulomb: null pointer");
     OdqdPlan plan;
     int rc = make_odqd_plan(l, Gp, &plan);
     if (rc) return rc;
@@ -81,14 +93,17 @@ extern "C" int qs_odqd_coulomb(const double* Cmat, const double* grid, double al
     QS_LAUNCH_CHECK();
 
     const int64_t L2 = l * l;
+    const int64_t rows = (a_end - a_begin) * l;  // the (a_loc, c) rows of T this call needs
     if ((rc = qs_build_coulomb_image(grid, alpha, a, Gp, img1, stream))) return rc;
-    // Tt[q, (ac)]: rows x = (ac), new index w = q stored slowest
-    if ((rc = qs_quarter_transform(D, QS_F64, L2, Gp, plan.pitch, img1, QS_F64, Gp, Tt, L2, 1, 0, 1, 0, L2, stream)))
+    // Tt[q, (a_loc c)]: rows x = (a_loc, c) of D, new index w = q stored slowest
+    if ((rc = qs_quarter_transform(D + a_begin * l * plan.pitch, QS_F64, rows, Gp, plan.pitch, img1, QS_F64, Gp, Tt,
+                                   rows, 1, 0, 1, 0, rows, stream)))
         return rc;
-    // M[k = q, w = (ac)] = Tt[q * l^2 + (ac)]
-    if ((rc = qs_build_coeff_image(Tt, QS_F64, L2, 1, 0, Gp, L2, QS_F64, img2, stream))) return rc;
-    // u[a,b,c,d]: x = (b,d) -> b*l^2 + d ; w = (a,c) -> a*l^3 + c*l
-    if ((rc = qs_quarter_transform(D, QS_F64, L2, Gp, plan.pitch, img2, QS_F64, L2, u_out, l, 1, L2, l, l, L2 * l, stream)))
+    // M[k = q, w = (a_loc c)] = Tt[q * rows + (a_loc c)]
+    if ((rc = qs_build_coeff_image(Tt, QS_F64, rows, 1, 0, Gp, rows, QS_F64, img2, stream))) return rc;
+    // u[a_loc,b,c,d]: x = (b,d) -> b*l^2 + d ; w = (a_loc,c) -> a_loc*l^3 + c*l
+    if ((rc = qs_quarter_transform(D, QS_F64, L2, Gp, plan.pitch, img2, QS_F64, rows, u_out, l, 1, L2, l, l, L2 * l,
+                                   stream)))
         return rc;
     return QS_OK;
 }

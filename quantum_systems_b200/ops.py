@@ -150,20 +150,29 @@ def quarter_transform(A, X, K, lda, image, m_dtype, W, out, x_inner, sx0, sx1, w
     return out
 
 
-def add_spin_two_body(u, anti_symmetrize=False, out_dtype=None, planes=None, out=None):
+def add_spin_two_body(u, anti_symmetrize=False, out_dtype=None, planes=None, out=None, first_spatial_plane=0):
     """Spin-double ``u`` (l,l,l,l) -> (2l,2l,2l,2l), optionally fused with the anti-symmetrisation
     and the widening cast (reference basis_set.py:772-778, :298-319).  ``planes=(P0, P1)`` restricts
-    the leading spin-orbital index (multi-GPU shard); the result then has ``P1 - P0`` leading planes."""
+    the leading spin-orbital index (multi-GPU shard); the result then has ``P1 - P0`` leading planes.
+    A rank that holds only the spatial planes it needs passes that slab ``u[first_spatial_plane : ...]``
+    (shape ``(planes, l, l, l)``) with ``first_spatial_plane``; it must cover ``P0 // 2 .. (P1 - 1) // 2``."""
     u = _device_tensor(u, "u")
-    l = u.shape[0]
-    if tuple(u.shape) != (l, l, l, l):
-        raise ValueError(f"u must be (l,l,l,l), got {tuple(u.shape)}")
+    l = u.shape[-1]
+    if u.dim() != 4 or tuple(u.shape[1:]) != (l, l, l):
+        raise ValueError(f"u must be (planes,l,l,l), got {tuple(u.shape)}")
     out_dtype = u.dtype if out_dtype is None else out_dtype
     p0, p1 = (0, 2 * l) if planes is None else planes
+    if p1 > p0 and not (first_spatial_plane <= p0 // 2 and (p1 - 1) // 2 < first_spatial_plane + u.shape[0]):
+        raise ValueError(
+            f"spin planes [{p0}, {p1}) need spatial planes [{p0 // 2}, {(p1 - 1) // 2 + 1}), the slab holds "
+            f"[{first_spatial_plane}, {first_spatial_plane + u.shape[0]})"
+        )
     if out is None:
         out = torch.empty((p1 - p0, 2 * l, 2 * l, 2 * l), dtype=out_dtype, device=u.device)
+    # the kernel addresses spatial plane p at base + p * l^3: hand it the (virtual) base of the whole tensor
+    base = ctypes.c_void_p(u.data_ptr() - first_spatial_plane * l**3 * u.element_size())
     _native.call(
-        "qs_add_spin_two_body", _ptr(u), _code(u), l, _ptr(out), _DTYPES[out_dtype], int(bool(anti_symmetrize)), p0,
+        "qs_add_spin_two_body", base, _code(u), l, _ptr(out), _DTYPES[out_dtype], int(bool(anti_symmetrize)), p0,
         p1, _stream(),
     )
     return out
@@ -220,9 +229,10 @@ def fock_spatial(h, u, n_occ, f=None):
     return _fock("qs_fock_spatial", h, u, n_occ, f)
 
 
-def odqd_coulomb(C, inner_grid, alpha, a):
+def odqd_coulomb(C, inner_grid, alpha, a, planes=None):
     """Grid Coulomb elements ``u_abcd`` of the 1-D quantum dot (reference one_dim_qd.py:275-280).
-    ``C``: (G', l) eigenvectors on the interior grid; ``inner_grid``: (G',)."""
+    ``C``: (G', l) eigenvectors on the interior grid; ``inner_grid``: (G',).  ``planes=(a0, a1)`` builds only the
+    leading-index planes ``u[a0:a1]`` (multi-GPU shard; no communication)."""
     C = _device_tensor(C, "C")
     inner_grid = _device_tensor(inner_grid, "inner_grid")
     if C.dtype != torch.float64 or inner_grid.dtype != torch.float64:
@@ -230,13 +240,14 @@ def odqd_coulomb(C, inner_grid, alpha, a):
     Gp, l = C.shape
     if tuple(inner_grid.shape) != (Gp,):
         raise ValueError("inner_grid must have one entry per row of C")
-    out = torch.empty((l, l, l, l), dtype=torch.float64, device=C.device)
+    a0, a1 = (0, l) if planes is None else planes
+    out = torch.empty((a1 - a0, l, l, l), dtype=torch.float64, device=C.device)
     nbytes = ctypes.c_int64(0)
     _native.call("qs_odqd_coulomb_workspace_bytes", l, Gp, ctypes.byref(nbytes))
     owner, ws = _workspace(nbytes.value, C.device)
     _native.call(
-        "qs_odqd_coulomb", _ptr(C), _ptr(inner_grid), float(alpha), float(a), l, Gp, _ptr(out), ws, nbytes.value,
-        _stream(),
+        "qs_odqd_coulomb_planes", _ptr(C), _ptr(inner_grid), float(alpha), float(a), l, Gp, _ptr(out), a0, a1, ws,
+        nbytes.value, _stream(),
     )
     owner.record_stream(torch.cuda.current_stream())
     return out

@@ -604,6 +604,16 @@ def transform_two_body_sharded(u, C, C_tilde=None):
     return result
 
 
+def odqd_spatial_planes(C, inner_grid, alpha=1.0, a=0.25):
+    """Plane builder for :meth:`ShardedBasisSet.from_spatial_planes`: the shielded-Coulomb elements of a 1-D
+    quantum dot (reference one_dim_qd.py:275-280) for leading-index planes ``[p0, p1)`` only -- ``C`` (G', l) and
+    the interior grid are replicated, each rank runs the two DMMA GEMMs for its own rows of ``T = D W``."""
+    from . import _arrays, ops
+
+    C_dev, grid_dev = _arrays.to_device(C), _arrays.to_device(inner_grid)
+    return lambda p0, p1: ops.odqd_coulomb(C_dev, grid_dev, alpha, a, planes=(p0, p1))
+
+
 # ------------------------------------------------------------------------------------------------
 # the reference-facing container, sharded
 # ------------------------------------------------------------------------------------------------
@@ -663,6 +673,32 @@ class ShardedBasisSet:
             if p1 > p0:
                 ops.add_spin_two_body(u_dev, anti_symmetrize=anti_symmetrize, out_dtype=out_dtype, planes=(p0, p1),
                                       out=u.local(r))
+        ctx.barrier()
+        h2 = ops.add_spin_one_body(_arrays.to_device(h), out_dtype=out_dtype)
+        s2 = ops.add_spin_one_body(_arrays.to_device(s), out_dtype=out_dtype)
+        return cls(ctx, n, h2, s2, u, includes_spin=True, anti_symmetrized_u=bool(anti_symmetrize))
+
+    @classmethod
+    def from_spatial_planes(cls, ctx, h, s, l, spatial_planes, anti_symmetrize=True, out_dtype=torch.complex128):
+        """Like :meth:`from_spatial`, but no rank ever holds the whole spatial tensor: ``spatial_planes(p0, p1)``
+        returns (builds) the planes ``u_spatial[p0:p1]`` as a ``(p1 - p0, l, l, l)`` device tensor, and every rank
+        asks only for the planes behind its own spin-orbital planes ``P = 2p + sigma``.  With
+        :func:`odqd_spatial_planes` the grid Coulomb build itself is sharded: ODQD build ->
+        add_spin + anti-symmetrise -> change_basis without a replicated l^4 tensor and without communication
+        before the transform."""
+        from . import _arrays, ops
+
+        n = 2 * l
+        u = ShardedTwoBody.empty(ctx, n, out_dtype)
+        for r in ctx.local_ranks:
+            p0, p1 = u.planes(r)
+            if p1 > p0:
+                sp0, sp1 = p0 // 2, (p1 - 1) // 2 + 1
+                slab = _arrays.to_device(spatial_planes(sp0, sp1))
+                if slab.is_complex() and out_dtype != torch.complex128:
+                    raise TypeError("complex spatial integrals need a complex128 sharded tensor")
+                ops.add_spin_two_body(slab, anti_symmetrize=anti_symmetrize, out_dtype=out_dtype, planes=(p0, p1),
+                                      out=u.local(r), first_spatial_plane=sp0)
         ctx.barrier()
         h2 = ops.add_spin_one_body(_arrays.to_device(h), out_dtype=out_dtype)
         s2 = ops.add_spin_one_body(_arrays.to_device(s), out_dtype=out_dtype)

@@ -109,3 +109,50 @@ def test_two_gpu_processes(exchange):
     proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
     assert "MULTI_GPU_OK" in proc.stdout
+
+
+@pytest.mark.parametrize("l,G", [(6, 101), (7, 64), (10, 201)])
+def test_odqd_build_by_planes(l, G):
+    """The grid Coulomb build restricted to leading-index planes tiles the full build."""
+    from quantum_systems_b200 import ops
+
+    grid, eps, C = oracle.odqd_orbitals(l, 5.0, G, lambda x: 0.5 * x**2)
+    expected = np.ascontiguousarray(oracle.odqd_coulomb_elements(C, grid, 1.0, 0.25))
+    C_dev, grid_dev = dev(C), dev(grid[1:-1])
+    whole = ops.odqd_coulomb(C_dev, grid_dev, 1.0, 0.25)
+    assert_close_scaled(whole.cpu().numpy(), expected)
+    cuts = [0, 1, 1, l // 2, l]
+    parts = [ops.odqd_coulomb(C_dev, grid_dev, 1.0, 0.25, planes=(a0, a1)) for a0, a1 in zip(cuts, cuts[1:])]
+    assert parts[1].shape[0] == 0
+    assert_close_scaled(torch.cat(parts).cpu().numpy(), expected)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 5])
+@pytest.mark.parametrize("out_complex", [False, True])
+def test_sharded_odqd_pipeline_without_a_replicated_tensor(world, out_complex):
+    """ODQD build -> add_spin + anti-symmetrise -> change_basis, every stage sharded (emulated ranks): no rank holds
+    the spatial l^4 tensor, each builds only the planes behind its own spin-orbital planes."""
+    from quantum_systems_b200 import sharded
+
+    l, G = 7, 101
+    grid, eps, C = oracle.odqd_orbitals(l, 5.0, G, lambda x: 0.5 * x**2)
+    u_spatial = oracle.odqd_coulomb_elements(C, grid, 1.0, 0.25)
+    h = np.diag(eps)
+    asked = []
+
+    def planes(p0, p1, build=sharded.odqd_spatial_planes(C, grid[1:-1], 1.0, 0.25)):
+        asked.append((p0, p1))
+        return build(p0, p1)
+
+    ctx = sharded.EmulatedContext(world)
+    dtype = torch.complex128 if out_complex else torch.float64
+    basis = sharded.ShardedBasisSet.from_spatial_planes(ctx, h, np.eye(l), l, planes, out_dtype=dtype)
+    expected = oracle.anti_symmetrize_u(oracle.add_spin_two_body(u_spatial))
+    got = basis.u.gather().cpu().numpy()
+    assert got.dtype == (np.complex128 if out_complex else np.float64)
+    assert_close_scaled(got, expected.astype(got.dtype))
+    assert all(p1 - p0 <= -(-(2 * l) // world) // 2 + 1 for p0, p1 in asked)  # only the needed planes were built
+    rng = np.random.default_rng(world)
+    Cb = np.linalg.qr(rng.standard_normal((2 * l, 2 * l)))[0]
+    basis.change_basis(dev(Cb))
+    assert_close_scaled(basis.u.gather().cpu().numpy(), oracle.transform_two_body_elements(expected, Cb).astype(got.dtype))
