@@ -56,6 +56,21 @@ void qs_timing_end(int slot, void* stream);
 // Number of SMs of the current device (cached).
 int qs_sm_count();
 
+// Internal (not part of the C ABI): symmetry mask of a quarter transform (see quarter_gemm.cu, tile_wanted) and
+// the masked launch used by the symmetry-aware four-index transform (transform.cu).
+struct QsTileMask {
+    int kind;             // 0 none; 1 column < row_lo; 2 row_hi < row_lo
+    int strict;           // 1: "<", 0: "<="
+    int64_t dh, mh, dl, ml;  // row_hi(x) = (x / dh) % mh, row_lo(x) = (x / dl) % ml
+};
+int64_t qs_tile_list_bytes(int64_t X, int64_t K, int64_t W, int a_dtype, int m_dtype);
+int qs_quarter_transform_masked(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda, const void* image,
+                                int m_dtype, int64_t W, void* out, int64_t x_inner, int64_t sx0, int64_t sx1,
+                                int64_t w_inner, int64_t sw0, int64_t sw1, const QsTileMask* mask, void* list_ws,
+                                void* stream);
+
+int qs_mirror_fill(void* out, int dtype, int64_t m, int mode, void* stream);
+
 // Internal (not part of the C ABI): coefficient image of the ODQD shielded-Coulomb matrix.
 int qs_build_coulomb_image(const double* grid, double alpha, double a, int64_t Gp, void* image, void* stream);
 

@@ -18,6 +18,8 @@
 //   * the epilogue writes the new index as the slowest axis (or any 2-level strided address).
 #include <stdlib.h>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace {
@@ -66,6 +68,10 @@ struct QuarterParams {
     // traffic of a launch is uniform in time (contiguous column ranges make every rank write to the same one or
     // two peers at once: measured +29 % on 7 of 8 ranks at n = 400).  deal_mul == 1: identity.
     uint32_t deal_mul, deal_mod;
+    // Optional tile list (symmetry-aware transforms): when non-null the launch visits only the n_listed linear
+    // tile ids (row_tile * tiles_w + col_tile, ascending) stored there instead of all tiles_x * tiles_w tiles.
+    const uint32_t* tile_list;
+    uint32_t n_listed;
 };
 
 __device__ __forceinline__ uint32_t dealt_column(uint32_t w, uint32_t mul, uint32_t mod) {
@@ -125,7 +131,7 @@ quarter_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const uint32_t total_tiles = p.tiles_x * (uint32_t)p.tiles_w;
+    const uint32_t total_tiles = p.tile_list ? p.n_listed : p.tiles_x * (uint32_t)p.tiles_w;
     const uint32_t my_tiles = blockIdx.x < total_tiles ? (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
     if (threadIdx.x == 0) {
@@ -152,7 +158,7 @@ quarter_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             const uint32_t bar_empty = bar_full + 8 * kStages;
             uint32_t j = 0;
             for (uint32_t i = pg; i < my_tiles; i += kGroups) {
-                const uint32_t tile = blockIdx.x + i * gridDim.x;
+                const uint32_t tile = p.tile_list ? p.tile_list[blockIdx.x + i * gridDim.x] : blockIdx.x + i * gridDim.x;
                 const uint32_t tw = tile % (uint32_t)p.tiles_w;
                 const int px0 = (int)((tile / (uint32_t)p.tiles_w) * kBlockX);
                 const double* img = p.image + (size_t)tw * p.nchunks * (kBTileBytes / 8);
@@ -216,7 +222,7 @@ quarter_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #endif
 
     for (uint32_t i = group; i < my_tiles; i += kGroups) {
-        const uint32_t tile = blockIdx.x + i * gridDim.x;
+        const uint32_t tile = p.tile_list ? p.tile_list[blockIdx.x + i * gridDim.x] : blockIdx.x + i * gridDim.x;
 
         double acc[4][NT][2];
 #pragma unroll
@@ -433,7 +439,7 @@ quarter_gemm_split_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const uint32_t total_tiles = p.tiles_x * (uint32_t)p.tiles_w;
+    const uint32_t total_tiles = p.tile_list ? p.n_listed : p.tiles_x * (uint32_t)p.tiles_w;
     const uint32_t my_tiles = blockIdx.x < total_tiles ? (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
     if (threadIdx.x == 0) {
@@ -459,7 +465,7 @@ quarter_gemm_split_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
             const uint32_t bar_empty = bar_full + 8 * kStages;
             uint32_t j = 0;
             for (uint32_t i = pg; i < my_tiles; i += kGroups) {
-                const uint32_t tile = blockIdx.x + i * gridDim.x;
+                const uint32_t tile = p.tile_list ? p.tile_list[blockIdx.x + i * gridDim.x] : blockIdx.x + i * gridDim.x;
                 const uint32_t tw = tile % (uint32_t)p.tiles_w;
                 const int px0 = (int)((tile / (uint32_t)p.tiles_w) * kBlockX);
                 const double* img = p.image + (size_t)tw * p.nchunks * (kBTileBytes / 8);
@@ -502,7 +508,7 @@ quarter_gemm_split_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
     };
 
     for (uint32_t i = group; i < my_tiles; i += kGroups) {
-        const uint32_t tile = blockIdx.x + i * gridDim.x;
+        const uint32_t tile = p.tile_list ? p.tile_list[blockIdx.x + i * gridDim.x] : blockIdx.x + i * gridDim.x;
 
         double re[4][NTC][2], im[4][NTC][2];
 #pragma unroll
@@ -777,7 +783,7 @@ int launch_variant(const CUtensorMap& map, const QuarterParams& p, cudaStream_t 
         QS_CUDA(cudaFuncSetAttribute(quarter_gemm_kernel<NT, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    const int64_t total = (int64_t)p.tiles_x * p.tiles_w;
+    const int64_t total = p.tile_list ? (int64_t)p.n_listed : (int64_t)p.tiles_x * p.tiles_w;
     const int64_t resident = qs_sm_count();  // one persistent CTA per SM
     const int64_t grid = total < resident ? total : resident;
     quarter_gemm_kernel<NT, CO><<<(unsigned)grid, kThreads, smem, st>>>(map, p);
@@ -809,7 +815,7 @@ int launch_split_variant(const CUtensorMap& map, const QuarterParams& p, cudaStr
         QS_CUDA(cudaFuncSetAttribute(quarter_gemm_split_kernel<NTC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    const int64_t total = (int64_t)p.tiles_x * p.tiles_w;
+    const int64_t total = p.tile_list ? (int64_t)p.n_listed : (int64_t)p.tiles_x * p.tiles_w;
     const int64_t resident = qs_sm_count();
     const int64_t grid = total < resident ? total : resident;
     quarter_gemm_split_kernel<NTC><<<(unsigned)grid, kThreads, smem, st>>>(map, p);
@@ -929,10 +935,34 @@ int qs_build_coulomb_image(const double* grid, double alpha, double a, int64_t G
 
 namespace {
 
+// Is any (row, column) of the CTA tile (rows [x0, x1], output columns [w0, w1]) wanted by the mask?
+//   kind 1: wanted iff column < row_lo (strict) or <= (not strict),  row_lo(x) = (x / dl) % ml
+//   kind 2: wanted iff row_hi < row_lo (or <=),  row_hi(x) = (x / dh) % mh,  dl divides dh
+// Conservative (never drops a wanted tile); exact when a tile does not straddle a block of the coarser index.
+bool tile_wanted(const QsTileMask& m, int64_t x0, int64_t x1, int64_t w0, int64_t w1) {
+    (void)w1;
+    const int64_t l0 = x0 / m.dl, l1 = x1 / m.dl;
+    int64_t lo_max;  // the largest row_lo inside the tile
+    if (l1 - l0 >= m.ml - 1 || (l1 % m.ml) < (l0 % m.ml)) lo_max = m.ml - 1;  // covers a whole period or wraps
+    else lo_max = l1 % m.ml;
+    if (m.kind == 1) return m.strict ? w0 < lo_max : w0 <= lo_max;
+    const int64_t h0 = x0 / m.dh, h1 = x1 / m.dh;
+    if (h1 > h0 + 1) return true;  // spans several values of the coarser index: keep
+    if (h1 == h0 + 1) {
+        // two blocks: the first runs to the end of its row_lo range, the second starts at row_lo = 0
+        const int64_t hi0 = h0 % m.mh, hi1 = h1 % m.mh, lo1 = l1 % m.ml;
+        const bool first = m.strict ? hi0 < m.ml - 1 : hi0 <= m.ml - 1;
+        const bool second = m.strict ? hi1 < lo1 : hi1 <= lo1;
+        return first || second;
+    }
+    const int64_t hi = h0 % m.mh;
+    return m.strict ? hi < lo_max : hi <= lo_max;
+}
+
 int quarter_launch(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda, const void* image, int m_dtype,
                    int64_t W, void* out, void* const* out_table, int64_t n_dest, int64_t x_inner, int64_t x_mid,
                    int64_t sx0, int64_t sx1, int64_t sx2, int64_t w_inner, int64_t sw0, int64_t sw1, int64_t w_deal,
-                   void* stream) {
+                   void* stream, const QsTileMask* mask = nullptr, void* list_ws = nullptr) {
     QS_REQUIRE(A && image && (out || out_table), "qs_quarter_transform: null pointer");
     QS_REQUIRE(w_deal >= 1 && w_deal < (W > 1 ? W : 2) && gcd64(w_deal, W) == 1,
                "qs_quarter_transform_scatter: the dealing multiplier %lld is not coprime to W = %lld",
@@ -982,13 +1012,49 @@ int quarter_launch(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda
     for (int64_t d = 0; d < n_dest; ++d) vec2 = vec2 && (reinterpret_cast<uintptr_t>(out_table[d]) & 15) == 0;
 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // symmetry mask: per tile group, the ascending list of wanted linear tile ids, staged into list_ws
+    std::vector<uint32_t> lists[2];
+    double wanted_fraction = 1.0;
+    if (mask && mask->kind) {
+        QS_REQUIRE(list_ws && w_deal == 1 && n_dest == 0, "internal: a masked quarter transform needs list space");
+        const int64_t tiles_x = qs_ceil_div(X, kBlockX);
+        const int cols_per_elem = (out_complex && !tl.split) ? 2 : 1;  // real columns per output element
+        int64_t all = 0, kept = 0;
+        for (int gi = 0; gi < tl.ngroups; ++gi) {
+            const TileGroup& gr = tl.group[gi];
+            for (int64_t rt = 0; rt < tiles_x; ++rt) {
+                const int64_t x0 = rt * kBlockX, x1 = (x0 + kBlockX < X ? x0 + kBlockX : X) - 1;
+                for (int ct = 0; ct < gr.tiles_w; ++ct) {
+                    const int64_t c0 = gr.w_first + (int64_t)ct * 8 * gr.NT;
+                    int64_t c1 = c0 + 8 * gr.NT - 1;
+                    if (c1 > tl.Wp - 1) c1 = tl.Wp - 1;
+                    ++all;
+                    if (tile_wanted(*mask, x0, x1, c0 / cols_per_elem, c1 / cols_per_elem)) {
+                        lists[gi].push_back((uint32_t)(rt * gr.tiles_w + ct));
+                        ++kept;
+                    }
+                }
+            }
+        }
+        wanted_fraction = all ? (double)kept / (double)all : 1.0;
+    }
     int span = -1;
     // issued flops; the split variant's Wp counts complex columns, each fed by Kp real multiply-adds per row
-    qs_timing_begin(QS_FAMILY_QUARTER_GEMM, 2.0 * (double)X * tl.Kp * tl.Wp, stream, &span);
+    qs_timing_begin(QS_FAMILY_QUARTER_GEMM, 2.0 * (double)X * tl.Kp * tl.Wp * wanted_fraction, stream, &span);
+    uint32_t* list_dev = static_cast<uint32_t*>(list_ws);
     for (int gi = 0; gi < tl.ngroups; ++gi) {
         const TileGroup& gr = tl.group[gi];
         QuarterParams p;
         memset(&p, 0, sizeof(p));
+        if (mask && mask->kind) {
+            if (lists[gi].empty()) continue;
+            // pageable source: the runtime stages the bytes before returning
+            QS_CUDA(cudaMemcpyAsync(list_dev, lists[gi].data(), lists[gi].size() * sizeof(uint32_t),
+                                    cudaMemcpyHostToDevice, st));
+            p.tile_list = list_dev;
+            p.n_listed = (uint32_t)lists[gi].size();
+            list_dev += (lists[gi].size() + 3) / 4 * 4;
+        }
         p.image = static_cast<const double*>(image) + gr.image_offset;
         p.out = static_cast<double*>(out);
         p.ndest = (int)n_dest;
@@ -1022,6 +1088,23 @@ int quarter_launch(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda
 }
 
 }  // namespace
+
+// Internal (common.cuh): a quarter transform restricted to the tiles a symmetry mask wants.  list_ws needs
+// qs_tile_list_bytes() bytes of device memory.
+int64_t qs_tile_list_bytes(int64_t X, int64_t K, int64_t W, int a_dtype, int m_dtype) {
+    const Tiling tl = make_tiling(K, W, a_dtype, m_dtype);
+    int64_t tiles = 0;
+    for (int gi = 0; gi < tl.ngroups; ++gi) tiles += qs_ceil_div(X, kBlockX) * tl.group[gi].tiles_w + 4;
+    return tiles * (int64_t)sizeof(uint32_t);
+}
+
+int qs_quarter_transform_masked(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda, const void* image,
+                                int m_dtype, int64_t W, void* out, int64_t x_inner, int64_t sx0, int64_t sx1,
+                                int64_t w_inner, int64_t sw0, int64_t sw1, const QsTileMask* mask, void* list_ws,
+                                void* stream) {
+    return quarter_launch(A, a_dtype, X, K, lda, image, m_dtype, W, out, nullptr, 0, x_inner, 0xFFFFFFFFLL, sx0, sx1, 0,
+                          w_inner, sw0, sw1, 1, stream, mask, list_ws);
+}
 
 extern "C" int qs_quarter_transform(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda, const void* image,
                                     int m_dtype, int64_t W, void* out, int64_t x_inner, int64_t sx0, int64_t sx1,

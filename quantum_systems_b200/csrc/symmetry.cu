@@ -1,0 +1,176 @@
+// Symmetries of the two-body tensor that the four-index transform can exploit (csrc/transform.cu):
+//
+//   antisymmetry in the last pair   u[p,q,r,s] = -u[p,q,s,r]   (every anti-symmetrised tensor, basis_set.py:776-778)
+//   particle-exchange symmetry      u[p,q,r,s] =  u[q,p,s,r]   (every physical interaction; RandomBasisSet builds it
+//                                                               in, random_basis.py:40-42)
+//
+// Both survive the basis change u' = (C~ x C~) u (C x C) for ANY C, C~, already half way through: after the two
+// ket contractions T2[r,s,a,b] is antisymmetric in (r,s), resp. T2[r,s,a,b] = T2[s,r,b,a].  So the second, third
+// and fourth quarter steps only need the pairs r < s (r <= s), and the other half of the result is its mirror image.
+//
+//   qs_two_body_symmetry : EXACT test of both properties on the device (every element read once, blocks stop early
+//                          once a counter-example is known) -- a promise such as BasisSet's anti_symmetrized_u flag
+//                          is never trusted for skipping work.
+//   qs_mirror_fill       : completes a result of which only r < s (r <= s) was computed.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kTile = 32;
+
+template <bool COMPLEX>
+struct Val {
+    double re, im;
+    static __device__ __forceinline__ Val load(const double* u, long long idx) {
+        if (COMPLEX) {
+            const double2 v = reinterpret_cast<const double2*>(u)[idx];
+            return {v.x, v.y};
+        }
+        return {u[idx], 0.0};
+    }
+};
+
+// linear index over tile pairs (tr <= ts) of a tiles x tiles grid
+__device__ __forceinline__ void tile_pair(int linear, int tiles, int& tr, int& ts) {
+    tr = 0;
+    int rem = linear;
+    while (rem >= tiles - tr) {
+        rem -= tiles - tr;
+        ++tr;
+    }
+    ts = tr + rem;
+}
+
+// MODE 1: u[p,q,r,s] == -u[p,q,s,r] for all p,q,r,s.  grid (tile pairs, q, p); every element is read once.
+// MODE 2: u[p,q,r,s] ==  u[q,p,s,r].  grid (tiles*tiles, q, p), planes p <= q only (the others exit).
+template <bool COMPLEX, int MODE>
+__global__ void __launch_bounds__(256) symmetry_check_kernel(const double* __restrict__ u, int n, int tiles,
+                                                             int* __restrict__ ok) {
+    if (*reinterpret_cast<volatile int*>(ok) == 0) return;  // a counter-example is known already
+    const int p = blockIdx.z, q = blockIdx.y;
+    int tr, ts;
+    if (MODE == 1) {
+        tile_pair(blockIdx.x, tiles, tr, ts);
+    } else {
+        if (p > q) return;
+        tr = blockIdx.x / tiles;
+        ts = blockIdx.x % tiles;
+    }
+    __shared__ double pre[kTile][kTile + 1], pim[COMPLEX ? kTile : 1][kTile + 1];
+    const int r0 = tr * kTile, s0 = ts * kTile;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const long long plane = ((long long)p * n + q) * n * n;
+    const long long partner = MODE == 1 ? plane : ((long long)q * n + p) * n * n;
+    // partner tile E[i][j] = u[partner plane, s0 + i, r0 + j]
+    for (int i = ty; i < kTile; i += 8)
+        if (s0 + i < n && r0 + tx < n) {
+            const Val<COMPLEX> v = Val<COMPLEX>::load(u, partner + (long long)(s0 + i) * n + r0 + tx);
+            pre[i][tx] = v.re;
+            if (COMPLEX) pim[i][tx] = v.im;
+        }
+    __syncthreads();
+    bool bad = false;
+    for (int i = ty; i < kTile; i += 8)
+        if (r0 + i < n && s0 + tx < n) {
+            const Val<COMPLEX> v = Val<COMPLEX>::load(u, plane + (long long)(r0 + i) * n + s0 + tx);
+            const double er = pre[tx][i], ei = COMPLEX ? pim[tx][i] : 0.0;
+            if (MODE == 1) bad |= (v.re != -er) || (COMPLEX && v.im != -ei);
+            else bad |= (v.re != er) || (COMPLEX && v.im != ei);
+        }
+    if (__syncthreads_or(bad) && tx == 0 && ty == 0) *ok = 0;
+}
+
+// Complete out[p,q,r,s] of which only r < s (MODE 1) or r <= s (MODE 2) holds valid data:
+//   MODE 1: out[p,q,s,r] = -out[p,q,r,s] (r < s), out[p,q,r,r] = 0
+//   MODE 2: out[q,p,s,r] =  out[p,q,r,s] (r < s), and out[q,p,r,r] = out[p,q,r,r] for p < q
+// grid (tile pairs tr <= ts, q, p); the block reads the valid tile (tr, ts) and writes the mirrored tile (ts, tr).
+template <bool COMPLEX, int MODE>
+__global__ void __launch_bounds__(256) mirror_fill_kernel(double* __restrict__ out, int n, int tiles) {
+    int tr, ts;
+    tile_pair(blockIdx.x, tiles, tr, ts);
+    const int p = blockIdx.z, q = blockIdx.y;
+    __shared__ double vre[kTile][kTile + 1], vim[COMPLEX ? kTile : 1][kTile + 1];
+    const int r0 = tr * kTile, s0 = ts * kTile;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const long long src = ((long long)p * n + q) * n * n;
+    const long long dst = MODE == 1 ? src : ((long long)q * n + p) * n * n;
+    for (int i = ty; i < kTile; i += 8)
+        if (r0 + i < n && s0 + tx < n) {
+            const Val<COMPLEX> v = Val<COMPLEX>::load(out, src + (long long)(r0 + i) * n + s0 + tx);
+            vre[i][tx] = v.re;
+            if (COMPLEX) vim[i][tx] = v.im;
+        }
+    __syncthreads();
+    const double sign = MODE == 1 ? -1.0 : 1.0;
+    // target element (s, r) = (s0 + i, r0 + tx) takes source (r, s) = (r0 + tx, s0 + i), valid iff r < s
+    for (int i = ty; i < kTile; i += 8) {
+        const int s = s0 + i, r = r0 + tx;
+        if (s >= n || r >= n) continue;
+        const long long at = dst + (long long)s * n + r;
+        if (r < s) {
+            if (COMPLEX) reinterpret_cast<double2*>(out)[at] = make_double2(sign * vre[tx][i], sign * vim[tx][i]);
+            else out[at] = sign * vre[tx][i];
+        } else if (MODE == 1 && r == s) {
+            if (COMPLEX) reinterpret_cast<double2*>(out)[at] = make_double2(0.0, 0.0);
+            else out[at] = 0.0;
+        } else if (MODE == 2 && r == s && p < q) {
+            // both out[p,q,r,r] and out[q,p,r,r] were computed; keep one so that the result is EXACTLY symmetric
+            // (the next basis change then finds the symmetry again)
+            if (COMPLEX) reinterpret_cast<double2*>(out)[at] = make_double2(vre[tx][i], vim[tx][i]);
+            else out[at] = vre[tx][i];
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int qs_two_body_symmetry(const void* u, int dtype, int64_t n, int* host_flags, void* device_scratch,
+                                    void* stream) {
+    QS_REQUIRE(u && host_flags && device_scratch && n > 0 && n <= 65535, "qs_two_body_symmetry: bad arguments");
+    QS_REQUIRE(dtype == QS_F64 || dtype == QS_C128, "qs_two_body_symmetry: bad dtype");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int* ok = static_cast<int*>(device_scratch);
+    const int tiles = (int)qs_ceil_div(n, kTile);
+    const dim3 block(32, 8);
+    const double* up = static_cast<const double*>(u);
+    int result[2] = {1, 1};
+    QS_CUDA(cudaMemcpyAsync(ok, result, sizeof(result), cudaMemcpyHostToDevice, st));
+    const dim3 grid1((unsigned)(tiles * (tiles + 1) / 2), (unsigned)n, (unsigned)n);
+    const dim3 grid2((unsigned)(tiles * tiles), (unsigned)n, (unsigned)n);
+    if (dtype == QS_C128) {
+        symmetry_check_kernel<true, 1><<<grid1, block, 0, st>>>(up, (int)n, tiles, ok);
+        QS_LAUNCH_CHECK();
+        symmetry_check_kernel<true, 2><<<grid2, block, 0, st>>>(up, (int)n, tiles, ok + 1);
+    } else {
+        symmetry_check_kernel<false, 1><<<grid1, block, 0, st>>>(up, (int)n, tiles, ok);
+        QS_LAUNCH_CHECK();
+        symmetry_check_kernel<false, 2><<<grid2, block, 0, st>>>(up, (int)n, tiles, ok + 1);
+    }
+    QS_LAUNCH_CHECK();
+    QS_CUDA(cudaMemcpyAsync(result, ok, sizeof(result), cudaMemcpyDeviceToHost, st));
+    QS_CUDA(cudaStreamSynchronize(st));
+    *host_flags = (result[0] ? 1 : 0) | (result[1] ? 2 : 0);
+    return QS_OK;
+}
+
+// Internal (common.cuh): mode 1 antisymmetric fill, mode 2 particle-exchange fill of an (m,m,m,m) result.
+int qs_mirror_fill(void* out, int dtype, int64_t m, int mode, void* stream) {
+    QS_REQUIRE(out && m > 0 && m <= 65535 && (mode == 1 || mode == 2), "qs_mirror_fill: bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int tiles = (int)qs_ceil_div(m, kTile);
+    const dim3 block(32, 8);
+    const dim3 grid((unsigned)(tiles * (tiles + 1) / 2), (unsigned)m, (unsigned)m);
+    double* o = static_cast<double*>(out);
+    int span = -1;
+    qs_timing_begin(QS_FAMILY_SPIN_PASS, (double)m * m * m * m * 8.0 * qs_elem_doubles(dtype), stream, &span);
+    if (dtype == QS_C128) {
+        if (mode == 1) mirror_fill_kernel<true, 1><<<grid, block, 0, st>>>(o, (int)m, tiles);
+        else mirror_fill_kernel<true, 2><<<grid, block, 0, st>>>(o, (int)m, tiles);
+    } else {
+        if (mode == 1) mirror_fill_kernel<false, 1><<<grid, block, 0, st>>>(o, (int)m, tiles);
+        else mirror_fill_kernel<false, 2><<<grid, block, 0, st>>>(o, (int)m, tiles);
+    }
+    QS_LAUNCH_CHECK();
+    qs_timing_end(span, stream);
+    return QS_OK;
+}

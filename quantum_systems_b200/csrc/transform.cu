@@ -16,7 +16,7 @@ namespace {
 struct TwoBodyPlan {
     int t_dtype;  // dtype of every intermediate and of the result
     int64_t pitch_u, pitch_t;
-    int64_t pad_bytes, bufA_bytes, bufB_bytes, img_bytes[2], total;
+    int64_t pad_bytes, bufA_bytes, bufB_bytes, img_bytes[2], list_bytes, total;
 };
 
 int64_t padded_pitch(int64_t n, int dtype) { return dtype == QS_C128 ? n : n + (n & 1); }
@@ -38,8 +38,16 @@ int make_plan(int64_t n, int64_t m, int u_dtype, int c_dtype, TwoBodyPlan* plan)
     if (rc) return rc;
     plan->img_bytes[0] = qs_round_up(plan->img_bytes[0], 1024);
     plan->img_bytes[1] = qs_round_up(plan->img_bytes[1], 1024);
+    // tile lists of the symmetry-aware variant (steps 2-4), a few hundred KB at most
+    int64_t lists = qs_tile_list_bytes(m * n * n, n, m, plan->t_dtype, c_dtype);
+    const int64_t l3 = qs_tile_list_bytes(m * m * n, n, m, plan->t_dtype, c_dtype);
+    const int64_t l4 = qs_tile_list_bytes(m * m * m, n, m, plan->t_dtype, c_dtype);
+    lists = lists > l3 ? lists : l3;
+    lists = lists > l4 ? lists : l4;
+    plan->list_bytes = qs_round_up(lists, 1024);
     // images: [C for step 1][C for step 2][Ct^T for steps 3, 4]
-    plan->total = plan->pad_bytes + plan->bufA_bytes + plan->bufB_bytes + plan->img_bytes[0] + 2 * plan->img_bytes[1];
+    plan->total = plan->pad_bytes + plan->bufA_bytes + plan->bufB_bytes + plan->img_bytes[0] + 2 * plan->img_bytes[1] +
+                  plan->list_bytes;
     return QS_OK;
 }
 
@@ -74,6 +82,14 @@ int rotated_quarter(const void* A, int a_dtype, int64_t X, int64_t K, int64_t ld
                                 stream);
 }
 
+int masked_rotated_quarter(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda, const void* image,
+                           int m_dtype, int64_t W, void* out, int64_t lo_extent, int64_t lo_pitch,
+                           const QsTileMask* mask, void* list_ws, void* stream) {
+    const int64_t plane = X / lo_extent * lo_pitch;
+    return qs_quarter_transform_masked(A, a_dtype, X, K, lda, image, m_dtype, W, out, lo_extent, 1, lo_pitch, 1, 0,
+                                       plane, mask, list_ws, stream);
+}
+
 }  // namespace
 
 extern "C" int qs_pad_rows(const void* in, void* out, int64_t rows, int64_t n, int64_t pitch, int dtype, void* stream) {
@@ -95,8 +111,20 @@ extern "C" int qs_transform_two_body_workspace_bytes(int64_t n, int64_t n_new, i
 extern "C" int qs_transform_two_body(const void* u, int u_dtype, const void* C, const void* Ct, int c_dtype, int64_t n,
                                      int64_t n_new, void* out, void* workspace, int64_t workspace_bytes,
                                      void* stream) {
+    return qs_transform_two_body_symmetric(u, u_dtype, C, Ct, c_dtype, n, n_new, 0, out, workspace, workspace_bytes,
+                                           stream);
+}
+
+// symmetry = 0: no assumption.  symmetry = 1: u[p,q,r,s] = -u[p,q,s,r]; symmetry = 2: u[p,q,r,s] = u[q,p,s,r] (the
+// caller has verified it with qs_two_body_symmetry).  After the two ket contractions T2[r,s,a,b] inherits the
+// symmetry in (r,s), so steps 2-4 visit only the tiles that hold a pair r < s (r <= s) and the other half of the
+// result is filled in by its mirror image (csrc/symmetry.cu).
+extern "C" int qs_transform_two_body_symmetric(const void* u, int u_dtype, const void* C, const void* Ct, int c_dtype,
+                                               int64_t n, int64_t n_new, int symmetry, void* out, void* workspace,
+                                               int64_t workspace_bytes, void* stream) {
     QS_REQUIRE(u && C && out && workspace, "qs_transform_two_body: null pointer");
     QS_REQUIRE(n > 0 && n_new > 0, "qs_transform_two_body: bad extents");
+    QS_REQUIRE(symmetry >= 0 && symmetry <= 2, "qs_transform_two_body: unknown symmetry %d", symmetry);
     TwoBodyPlan plan;
     int rc = make_plan(n, n_new, u_dtype, c_dtype, &plan);
     if (rc) return rc;
@@ -112,6 +140,7 @@ extern "C" int qs_transform_two_body(const void* u, int u_dtype, const void* C, 
     void* img1 = static_cast<char*>(bufB) + plan.bufB_bytes;
     void* img2 = static_cast<char*>(img1) + plan.img_bytes[0];
     void* img3 = static_cast<char*>(img2) + plan.img_bytes[1];
+    void* lists = static_cast<char*>(img3) + plan.img_bytes[1];
     const int td = plan.t_dtype;
 
     // M[k, w] = C[k, w] (row-major n x m) for steps 1-2
@@ -130,10 +159,23 @@ extern "C" int qs_transform_two_body(const void* u, int u_dtype, const void* C, 
     }
     // T1[s,a,b,c] ; T2[r,s,a,b] ; T3[q,r,s,a] (last axis at pitch P) ; out[p,q,r,s] dense
     if ((rc = rotated_quarter(a0, u_dtype, N * N * N, N, plan.pitch_u, img1, c_dtype, M, bufA, N, P, stream))) return rc;
-    if ((rc = rotated_quarter(bufA, td, M * N * N, N, P, img2, c_dtype, M, bufB, N, P, stream))) return rc;
-    if ((rc = rotated_quarter(bufB, td, M * M * N, N, P, img3, c_dtype, M, bufA, N, P, stream))) return rc;
-    if ((rc = rotated_quarter(bufA, td, M * M * M, N, P, img3, c_dtype, M, out, M, M, stream))) return rc;
-    return QS_OK;
+    if (!symmetry) {
+        if ((rc = rotated_quarter(bufA, td, M * N * N, N, P, img2, c_dtype, M, bufB, N, P, stream))) return rc;
+        if ((rc = rotated_quarter(bufB, td, M * M * N, N, P, img3, c_dtype, M, bufA, N, P, stream))) return rc;
+        if ((rc = rotated_quarter(bufA, td, M * M * M, N, P, img3, c_dtype, M, out, M, M, stream))) return rc;
+        return QS_OK;
+    }
+    const int strict = symmetry == 1;  // antisymmetry: the diagonal r = s vanishes, only r < s is computed
+    // step 2: rows (s, a, b), new column r -- wanted iff r < s
+    const QsTileMask m2 = {1, strict, 1, 1, N * N, M};
+    // step 3: rows (r, s, a) -- wanted iff r < s
+    const QsTileMask m3 = {2, strict, M * N, M, N, M};
+    // step 4: rows (q, r, s) -- wanted iff r < s
+    const QsTileMask m4 = {2, strict, M, M, 1, M};
+    if ((rc = masked_rotated_quarter(bufA, td, M * N * N, N, P, img2, c_dtype, M, bufB, N, P, &m2, lists, stream))) return rc;
+    if ((rc = masked_rotated_quarter(bufB, td, M * M * N, N, P, img3, c_dtype, M, bufA, N, P, &m3, lists, stream))) return rc;
+    if ((rc = masked_rotated_quarter(bufA, td, M * M * M, N, P, img3, c_dtype, M, out, M, M, &m4, lists, stream))) return rc;
+    return qs_mirror_fill(out, td, M, symmetry, stream);
 }
 
 extern "C" int qs_transform_one_body_workspace_bytes(int64_t n, int64_t n_new, int h_dtype, int c_dtype,

@@ -79,21 +79,53 @@ def real_coefficients_if_exact(u_is_complex, C, C_tilde):
     return C.real.contiguous(), (C_tilde.real.contiguous() if C_tilde is not None else None)
 
 
-def transform_two_body(u, C, C_tilde=None):
-    """``u'_pqrs = sum C~[p,a] C~[q,b] u[a,b,c,d] C[c,r] C[d,s]`` (reference basis_set.py:336-350)."""
+# below this extent the symmetry test costs more than the tiles it saves
+SYMMETRY_MIN_N = 48
+ANTISYMMETRIC_LAST_PAIR = 1  # u[p,q,r,s] = -u[p,q,s,r]
+PARTICLE_EXCHANGE = 2        # u[p,q,r,s] =  u[q,p,s,r]
+
+
+def two_body_symmetry(u):
+    """Exact device-side test of the two symmetries the transform can exploit; returns a bit mask of
+    ``ANTISYMMETRIC_LAST_PAIR`` and ``PARTICLE_EXCHANGE``.  Reads ``u`` once, stops at the first counter-example,
+    synchronises the stream."""
+    u = _device_tensor(u, "u")
+    n = u.shape[0]
+    if tuple(u.shape) != (n, n, n, n):
+        raise ValueError(f"u must be (n,n,n,n), got {tuple(u.shape)}")
+    flags = ctypes.c_int(0)
+    scratch = torch.empty(2, dtype=torch.int32, device=u.device)
+    _native.call("qs_two_body_symmetry", _ptr(u), _code(u), n, ctypes.byref(flags), _ptr(scratch), _stream())
+    return flags.value
+
+
+def transform_two_body(u, C, C_tilde=None, symmetry=None):
+    """``u'_pqrs = sum C~[p,a] C~[q,b] u[a,b,c,d] C[c,r] C[d,s]`` (reference basis_set.py:336-350).
+
+    ``symmetry=None`` (default) tests ``u`` for exact anti-symmetry in its last pair and for particle-exchange
+    symmetry (``two_body_symmetry``) and, if one holds, skips the tiles of quarter steps 2-4 that only hold mirror
+    images (``qs_transform_two_body_symmetric``); ``symmetry=0`` forces the plain four full steps."""
     u = _device_tensor(u, "u")
     C, C_tilde = _coefficients(C, C_tilde)
     C, C_tilde = real_coefficients_if_exact(u.is_complex(), C, C_tilde)
     n, m = C.shape
     if tuple(u.shape) != (n, n, n, n):
         raise ValueError(f"u must have shape {(n,) * 4} to be contracted with C {tuple(C.shape)}, got {tuple(u.shape)}")
+    if symmetry is None:
+        symmetry = 0
+        if min(n, m) >= SYMMETRY_MIN_N:
+            flags = two_body_symmetry(u)
+            symmetry = (
+                ANTISYMMETRIC_LAST_PAIR if flags & ANTISYMMETRIC_LAST_PAIR
+                else PARTICLE_EXCHANGE if flags & PARTICLE_EXCHANGE else 0
+            )
     out = torch.empty((m, m, m, m), dtype=_result_dtype(u, C), device=u.device)
     nbytes = ctypes.c_int64(0)
     _native.call("qs_transform_two_body_workspace_bytes", n, m, _code(u), _code(C), ctypes.byref(nbytes))
     owner, ws = _workspace(nbytes.value, u.device)
     _native.call(
-        "qs_transform_two_body", _ptr(u), _code(u), _ptr(C), _ptr(C_tilde), _code(C), n, m, _ptr(out), ws,
-        nbytes.value, _stream(),
+        "qs_transform_two_body_symmetric", _ptr(u), _code(u), _ptr(C), _ptr(C_tilde), _code(C), n, m, int(symmetry),
+        _ptr(out), ws, nbytes.value, _stream(),
     )
     owner.record_stream(torch.cuda.current_stream())
     return out
