@@ -59,12 +59,13 @@ int qs_transform_two_body(const void* u, int u_dtype, const void* C, const void*
  *   bit 0 (1): u[p,q,r,s] = -u[p,q,s,r]   every anti-symmetrised tensor (basis_set.py:776-778)
  *   bit 1 (2): u[p,q,r,s] =  u[q,p,s,r]   particle exchange, every physical interaction (random_basis.py:40-42)
  * qs_two_body_symmetry tests both EXACTLY on the device (one read of u, early exit on the first counter-example;
- * it synchronises the stream to return the flags in *host_flags; device_scratch: 8 bytes).
+ * it synchronises the stream to return the flags in *host_flags; device_scratch: 8 bytes; first_match != 0 skips
+ * the second test when the first holds and then reports bit 0 only).
  * qs_transform_two_body_symmetric(symmetry = 1 or 2) then runs quarter steps 2-4 only on the tiles that hold a
  * pair r < s (r <= s) -- about 45 % fewer tensor-core flops at n = 128, approaching 3/8 for large n -- and completes
  * the result with its mirror image.  symmetry = 0 is qs_transform_two_body.  Same workspace as the plain call. */
-int qs_two_body_symmetry(const void* u, int dtype, int64_t n, int* host_flags, void* device_scratch,
-                         void* stream);
+int qs_two_body_symmetry(const void* u, int dtype, int64_t n, int first_match, int* host_flags,
+                         void* device_scratch, void* stream);
 int qs_transform_two_body_symmetric(const void* u, int u_dtype, const void* C, const void* Ct,
                                     int c_dtype, int64_t n, int64_t n_new, int symmetry, void* out,
                                     void* workspace, int64_t workspace_bytes, void* stream);

@@ -26,7 +26,7 @@ SIGNATURES = {
     "qs_last_error": [],
     "qs_transform_two_body_workspace_bytes": [_i64, _i64, _int, _int, ctypes.POINTER(_i64)],
     "qs_transform_two_body": [_ptr, _int, _ptr, _ptr, _int, _i64, _i64, _ptr, _ptr, _i64, _ptr],
-    "qs_two_body_symmetry": [_ptr, _int, _i64, ctypes.POINTER(_int), _ptr, _ptr],
+    "qs_two_body_symmetry": [_ptr, _int, _i64, _int, ctypes.POINTER(_int), _ptr, _ptr],
     "qs_transform_two_body_symmetric": [_ptr, _int, _ptr, _ptr, _int, _i64, _i64, _int, _ptr, _ptr, _i64, _ptr],
     "qs_coeff_image_bytes": [_i64, _i64, _int, _int, ctypes.POINTER(_i64)],
     "qs_build_coeff_image": [_ptr, _int, _i64, _i64, _int, _i64, _i64, _int, _ptr, _ptr],

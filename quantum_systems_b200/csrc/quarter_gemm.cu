@@ -72,6 +72,11 @@ struct QuarterParams {
     // tile ids (row_tile * tiles_w + col_tile, ascending) stored there instead of all tiles_x * tiles_w tiles.
     const uint32_t* tile_list;
     uint32_t n_listed;
+    // Optional row-offset tables (packed pair layouts of the symmetry-aware transform): with x = xq * x_inner + xr
+    // the row contributes xq_table[xq] instead of xq * sx1 (a negative entry drops the row: nothing is stored) and
+    // xr_table[xr] instead of xr * sx0.  Element offsets.
+    const long long* xq_table;
+    const long long* xr_table;
 };
 
 __device__ __forceinline__ uint32_t dealt_column(uint32_t w, uint32_t mul, uint32_t mod) {
@@ -341,11 +346,15 @@ quarter_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             xok[mt] = x < p.X;
             const uint32_t xq = x / p.x_inner;
             const uint32_t xr = x - xq * p.x_inner;
-            long long off = (long long)xr * p.sx0;
+            long long off = (p.xr_table && xok[mt]) ? p.xr_table[xr] : (long long)xr * p.sx0;
             if (p.x_mid != 0xFFFFFFFFu) {
                 const uint32_t x2 = xq / p.x_mid;
                 const uint32_t x1 = xq - x2 * p.x_mid;
                 off += (long long)x2 * p.sx2 + (long long)x1 * p.sx1;
+            } else if (p.xq_table && xok[mt]) {
+                const long long tq = p.xq_table[xq];
+                if (tq < 0) xok[mt] = false;  // a row the symmetry does not need
+                off += tq;
             } else {
                 off += (long long)xq * p.sx1;
             }
@@ -587,11 +596,15 @@ quarter_gemm_split_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
             xok[mt] = x < p.X;
             const uint32_t xq = x / p.x_inner;
             const uint32_t xr = x - xq * p.x_inner;
-            long long off = (long long)xr * p.sx0;
+            long long off = (p.xr_table && xok[mt]) ? p.xr_table[xr] : (long long)xr * p.sx0;
             if (p.x_mid != 0xFFFFFFFFu) {
                 const uint32_t x2 = xq / p.x_mid;
                 const uint32_t x1 = xq - x2 * p.x_mid;
                 off += (long long)x2 * p.sx2 + (long long)x1 * p.sx1;
+            } else if (p.xq_table && xok[mt]) {
+                const long long tq = p.xq_table[xq];
+                if (tq < 0) xok[mt] = false;  // a row the symmetry does not need
+                off += tq;
             } else {
                 off += (long long)xq * p.sx1;
             }
@@ -962,7 +975,8 @@ bool tile_wanted(const QsTileMask& m, int64_t x0, int64_t x1, int64_t w0, int64_
 int quarter_launch(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda, const void* image, int m_dtype,
                    int64_t W, void* out, void* const* out_table, int64_t n_dest, int64_t x_inner, int64_t x_mid,
                    int64_t sx0, int64_t sx1, int64_t sx2, int64_t w_inner, int64_t sw0, int64_t sw1, int64_t w_deal,
-                   void* stream, const QsTileMask* mask = nullptr, void* list_ws = nullptr) {
+                   void* stream, const QsTileMask* mask = nullptr, void* list_ws = nullptr,
+                   const long long* xq_table = nullptr, const long long* xr_table = nullptr) {
     QS_REQUIRE(A && image && (out || out_table), "qs_quarter_transform: null pointer");
     QS_REQUIRE(w_deal >= 1 && w_deal < (W > 1 ? W : 2) && gcd64(w_deal, W) == 1,
                "qs_quarter_transform_scatter: the dealing multiplier %lld is not coprime to W = %lld",
@@ -1010,11 +1024,13 @@ int quarter_launch(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda
     int vec2 = !out_complex && sx0 == 1 && x_inner % 2 == 0 && X % 2 == 0 && sx1 % 2 == 0 && sx2 % 2 == 0 &&
                sw0 % 2 == 0 && (n_dest > 0 || sw1 % 2 == 0) && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
     for (int64_t d = 0; d < n_dest; ++d) vec2 = vec2 && (reinterpret_cast<uintptr_t>(out_table[d]) & 15) == 0;
+    if (xq_table || xr_table) vec2 = 0;  // tabulated row offsets: adjacent rows need not be adjacent in memory
 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // symmetry mask: per tile group, the ascending list of wanted linear tile ids, staged into list_ws
     std::vector<uint32_t> lists[2];
     double wanted_fraction = 1.0;
+    QS_REQUIRE(!(xq_table || xr_table) || n_dest == 0, "internal: row-offset tables and scattering do not combine");
     if (mask && mask->kind) {
         QS_REQUIRE(list_ws && w_deal == 1 && n_dest == 0, "internal: a masked quarter transform needs list space");
         const int64_t tiles_x = qs_ceil_div(X, kBlockX);
@@ -1077,6 +1093,8 @@ int quarter_launch(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda
         p.vec2 = vec2;
         p.deal_mul = (uint32_t)w_deal;
         p.deal_mod = (uint32_t)W;
+        p.xq_table = xq_table;
+        p.xr_table = xr_table;
         QS_REQUIRE((int64_t)p.tiles_x * p.tiles_w < (1LL << 31), "qs_quarter_transform: too many tiles");
         const int rc = tl.split      ? launch_split(gr.NT, map, p, st)
                        : out_complex ? launch_nt<true>(gr.NT, map, p, st)
@@ -1101,9 +1119,9 @@ int64_t qs_tile_list_bytes(int64_t X, int64_t K, int64_t W, int a_dtype, int m_d
 int qs_quarter_transform_masked(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda, const void* image,
                                 int m_dtype, int64_t W, void* out, int64_t x_inner, int64_t sx0, int64_t sx1,
                                 int64_t w_inner, int64_t sw0, int64_t sw1, const QsTileMask* mask, void* list_ws,
-                                void* stream) {
+                                const long long* xq_table, const long long* xr_table, void* stream) {
     return quarter_launch(A, a_dtype, X, K, lda, image, m_dtype, W, out, nullptr, 0, x_inner, 0xFFFFFFFFLL, sx0, sx1, 0,
-                          w_inner, sw0, sw1, 1, stream, mask, list_ws);
+                          w_inner, sw0, sw1, 1, stream, mask, list_ws, xq_table, xr_table);
 }
 
 extern "C" int qs_quarter_transform(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda, const void* image,

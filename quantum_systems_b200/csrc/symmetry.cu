@@ -41,43 +41,65 @@ __device__ __forceinline__ void tile_pair(int linear, int tiles, int& tr, int& t
     ts = tr + rem;
 }
 
-// MODE 1: u[p,q,r,s] == -u[p,q,s,r] for all p,q,r,s.  grid (tile pairs, q, p); every element is read once.
-// MODE 2: u[p,q,r,s] ==  u[q,p,s,r].  grid (tiles*tiles, q, p), planes p <= q only (the others exit).
+// MODE 1: u[p,q,r,s] == -u[p,q,s,r] for all p,q,r,s: work items (p, q, tile pair tr <= ts), every element read once.
+// MODE 2: u[p,q,r,s] ==  u[q,p,s,r]: work items (p <= q, tr, ts), every element read once.
+// Persistent blocks walk the work items and leave as soon as ANY block has found a counter-example, so a tensor
+// without the symmetry costs a few microseconds and only a symmetric one pays the full read of u.
 template <bool COMPLEX, int MODE>
 __global__ void __launch_bounds__(256) symmetry_check_kernel(const double* __restrict__ u, int n, int tiles,
-                                                             int* __restrict__ ok) {
-    if (*reinterpret_cast<volatile int*>(ok) == 0) return;  // a counter-example is known already
-    const int p = blockIdx.z, q = blockIdx.y;
-    int tr, ts;
-    if (MODE == 1) {
-        tile_pair(blockIdx.x, tiles, tr, ts);
-    } else {
-        if (p > q) return;
-        tr = blockIdx.x / tiles;
-        ts = blockIdx.x % tiles;
-    }
+                                                             long long items, int* __restrict__ ok) {
     __shared__ double pre[kTile][kTile + 1], pim[COMPLEX ? kTile : 1][kTile + 1];
-    const int r0 = tr * kTile, s0 = ts * kTile;
     const int tx = threadIdx.x, ty = threadIdx.y;
-    const long long plane = ((long long)p * n + q) * n * n;
-    const long long partner = MODE == 1 ? plane : ((long long)q * n + p) * n * n;
-    // partner tile E[i][j] = u[partner plane, s0 + i, r0 + j]
-    for (int i = ty; i < kTile; i += 8)
-        if (s0 + i < n && r0 + tx < n) {
-            const Val<COMPLEX> v = Val<COMPLEX>::load(u, partner + (long long)(s0 + i) * n + r0 + tx);
-            pre[i][tx] = v.re;
-            if (COMPLEX) pim[i][tx] = v.im;
+    const int per_plane = MODE == 1 ? tiles * (tiles + 1) / 2 : tiles * tiles;
+    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+        // block-uniform early exit (one thread polls the flag); also fences the shared tile of the previous item
+        if (__syncthreads_or(tx == 0 && ty == 0 && *reinterpret_cast<volatile int*>(ok) == 0)) return;
+        const int t = (int)(item % per_plane);
+        const long long pq = item / per_plane;
+        const int p = (int)(pq / n), q = (int)(pq % n);
+        int tr, ts;
+        if (MODE == 1) {
+            tile_pair(t, tiles, tr, ts);
+        } else {
+            if (p > q) continue;
+            tr = t / tiles;
+            ts = t % tiles;
         }
-    __syncthreads();
-    bool bad = false;
-    for (int i = ty; i < kTile; i += 8)
-        if (r0 + i < n && s0 + tx < n) {
-            const Val<COMPLEX> v = Val<COMPLEX>::load(u, plane + (long long)(r0 + i) * n + s0 + tx);
-            const double er = pre[tx][i], ei = COMPLEX ? pim[tx][i] : 0.0;
-            if (MODE == 1) bad |= (v.re != -er) || (COMPLEX && v.im != -ei);
-            else bad |= (v.re != er) || (COMPLEX && v.im != ei);
+        const int r0 = tr * kTile, s0 = ts * kTile;
+        const long long plane = ((long long)p * n + q) * n * n;
+        const long long partner = MODE == 1 ? plane : ((long long)q * n + p) * n * n;
+        // both tiles go to registers first (8 independent loads in flight per thread), then the partner tile
+        // E[i][j] = u[partner plane, s0 + i, r0 + j] is exchanged through shared memory
+        Val<COMPLEX> mine[kTile / 8], theirs[kTile / 8];
+#pragma unroll
+        for (int k = 0; k < kTile / 8; ++k) {
+            const int i = ty + 8 * k;
+            theirs[k] = (s0 + i < n && r0 + tx < n) ? Val<COMPLEX>::load(u, partner + (long long)(s0 + i) * n + r0 + tx)
+                                                     : Val<COMPLEX>{0.0, 0.0};
+            mine[k] = (r0 + i < n && s0 + tx < n) ? Val<COMPLEX>::load(u, plane + (long long)(r0 + i) * n + s0 + tx)
+                                                   : Val<COMPLEX>{0.0, 0.0};
         }
-    if (__syncthreads_or(bad) && tx == 0 && ty == 0) *ok = 0;
+#pragma unroll
+        for (int k = 0; k < kTile / 8; ++k) {
+            pre[ty + 8 * k][tx] = theirs[k].re;
+            if (COMPLEX) pim[ty + 8 * k][tx] = theirs[k].im;
+        }
+        __syncthreads();
+        bool bad = false;
+#pragma unroll
+        for (int k = 0; k < kTile / 8; ++k) {
+            const int i = ty + 8 * k;
+            if (r0 + i < n && s0 + tx < n) {
+                const double er = pre[tx][i], ei = COMPLEX ? pim[tx][i] : 0.0;
+                if (MODE == 1) bad |= (mine[k].re != -er) || (COMPLEX && mine[k].im != -ei);
+                else bad |= (mine[k].re != er) || (COMPLEX && mine[k].im != ei);
+            }
+        }
+        if (__syncthreads_or(bad)) {
+            if (tx == 0 && ty == 0) *ok = 0;
+            return;
+        }
+    }
 }
 
 // Complete out[p,q,r,s] of which only r < s (MODE 1) or r <= s (MODE 2) holds valid data:
@@ -124,8 +146,8 @@ __global__ void __launch_bounds__(256) mirror_fill_kernel(double* __restrict__ o
 
 }  // namespace
 
-extern "C" int qs_two_body_symmetry(const void* u, int dtype, int64_t n, int* host_flags, void* device_scratch,
-                                    void* stream) {
+extern "C" int qs_two_body_symmetry(const void* u, int dtype, int64_t n, int first_match, int* host_flags,
+                                    void* device_scratch, void* stream) {
     QS_REQUIRE(u && host_flags && device_scratch && n > 0 && n <= 65535, "qs_two_body_symmetry: bad arguments");
     QS_REQUIRE(dtype == QS_F64 || dtype == QS_C128, "qs_two_body_symmetry: bad dtype");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -135,17 +157,24 @@ extern "C" int qs_two_body_symmetry(const void* u, int dtype, int64_t n, int* ho
     const double* up = static_cast<const double*>(u);
     int result[2] = {1, 1};
     QS_CUDA(cudaMemcpyAsync(ok, result, sizeof(result), cudaMemcpyHostToDevice, st));
-    const dim3 grid1((unsigned)(tiles * (tiles + 1) / 2), (unsigned)n, (unsigned)n);
-    const dim3 grid2((unsigned)(tiles * tiles), (unsigned)n, (unsigned)n);
-    if (dtype == QS_C128) {
-        symmetry_check_kernel<true, 1><<<grid1, block, 0, st>>>(up, (int)n, tiles, ok);
-        QS_LAUNCH_CHECK();
-        symmetry_check_kernel<true, 2><<<grid2, block, 0, st>>>(up, (int)n, tiles, ok + 1);
-    } else {
-        symmetry_check_kernel<false, 1><<<grid1, block, 0, st>>>(up, (int)n, tiles, ok);
-        QS_LAUNCH_CHECK();
-        symmetry_check_kernel<false, 2><<<grid2, block, 0, st>>>(up, (int)n, tiles, ok + 1);
+    const long long items1 = (long long)n * n * (tiles * (tiles + 1) / 2), items2 = (long long)n * n * tiles * tiles;
+    const long long resident = (long long)qs_sm_count() * 8;  // 8 CTAs of 256 threads per SM
+    const unsigned grid1 = (unsigned)(items1 < resident ? items1 : resident);
+    const unsigned grid2 = (unsigned)(items2 < resident ? items2 : resident);
+    if (dtype == QS_C128) symmetry_check_kernel<true, 1><<<grid1, block, 0, st>>>(up, (int)n, tiles, items1, ok);
+    else symmetry_check_kernel<false, 1><<<grid1, block, 0, st>>>(up, (int)n, tiles, items1, ok);
+    QS_LAUNCH_CHECK();
+    if (first_match) {
+        // the caller will use the first symmetry that holds: do not pay for the second test if the first one passed
+        QS_CUDA(cudaMemcpyAsync(result, ok, sizeof(int), cudaMemcpyDeviceToHost, st));
+        QS_CUDA(cudaStreamSynchronize(st));
+        if (result[0]) {
+            *host_flags = 1;
+            return QS_OK;
+        }
     }
+    if (dtype == QS_C128) symmetry_check_kernel<true, 2><<<grid2, block, 0, st>>>(up, (int)n, tiles, items2, ok + 1);
+    else symmetry_check_kernel<false, 2><<<grid2, block, 0, st>>>(up, (int)n, tiles, items2, ok + 1);
     QS_LAUNCH_CHECK();
     QS_CUDA(cudaMemcpyAsync(result, ok, sizeof(result), cudaMemcpyDeviceToHost, st));
     QS_CUDA(cudaStreamSynchronize(st));

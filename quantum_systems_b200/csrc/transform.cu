@@ -6,6 +6,8 @@
 // Four launches of the same kernel "contract the last index, store the new index slowest":
 //   u[a,b,c,d] -C-> T1[s,a,b,c] -C-> T2[r,s,a,b] -Ct^T-> T3[q,r,s,a] -Ct^T-> out[p,q,r,s]
 // which is the reference's contraction order (s, r, q, p) with every transpose folded into a store.
+#include <vector>
+
 #include "common.cuh"
 
 namespace {
@@ -16,7 +18,7 @@ namespace {
 struct TwoBodyPlan {
     int t_dtype;  // dtype of every intermediate and of the result
     int64_t pitch_u, pitch_t;
-    int64_t pad_bytes, bufA_bytes, bufB_bytes, img_bytes[2], list_bytes, total;
+    int64_t pad_bytes, bufA_bytes, bufB_bytes, img_bytes[2], list_bytes, table_bytes, total;
 };
 
 int64_t padded_pitch(int64_t n, int dtype) { return dtype == QS_C128 ? n : n + (n & 1); }
@@ -45,9 +47,11 @@ int make_plan(int64_t n, int64_t m, int u_dtype, int c_dtype, TwoBodyPlan* plan)
     lists = lists > l3 ? lists : l3;
     lists = lists > l4 ? lists : l4;
     plan->list_bytes = qs_round_up(lists, 1024);
+    // row-offset tables of the packed pair layout: m^2 entries (step 3 rows -> pair slot) + m(m+1)/2 (pair -> r m + s)
+    plan->table_bytes = qs_round_up((m * m + m * (m + 1) / 2) * (int64_t)sizeof(long long), 1024);
     // images: [C for step 1][C for step 2][Ct^T for steps 3, 4]
     plan->total = plan->pad_bytes + plan->bufA_bytes + plan->bufB_bytes + plan->img_bytes[0] + 2 * plan->img_bytes[1] +
-                  plan->list_bytes;
+                  plan->list_bytes + plan->table_bytes;
     return QS_OK;
 }
 
@@ -87,7 +91,7 @@ int masked_rotated_quarter(const void* A, int a_dtype, int64_t X, int64_t K, int
                            const QsTileMask* mask, void* list_ws, void* stream) {
     const int64_t plane = X / lo_extent * lo_pitch;
     return qs_quarter_transform_masked(A, a_dtype, X, K, lda, image, m_dtype, W, out, lo_extent, 1, lo_pitch, 1, 0,
-                                       plane, mask, list_ws, stream);
+                                       plane, mask, list_ws, nullptr, nullptr, stream);
 }
 
 }  // namespace
@@ -141,6 +145,7 @@ extern "C" int qs_transform_two_body_symmetric(const void* u, int u_dtype, const
     void* img2 = static_cast<char*>(img1) + plan.img_bytes[0];
     void* img3 = static_cast<char*>(img2) + plan.img_bytes[1];
     void* lists = static_cast<char*>(img3) + plan.img_bytes[1];
+    long long* tables = reinterpret_cast<long long*>(static_cast<char*>(lists) + plan.list_bytes);
     const int td = plan.t_dtype;
 
     // M[k, w] = C[k, w] (row-major n x m) for steps 1-2
@@ -166,15 +171,37 @@ extern "C" int qs_transform_two_body_symmetric(const void* u, int u_dtype, const
         return QS_OK;
     }
     const int strict = symmetry == 1;  // antisymmetry: the diagonal r = s vanishes, only r < s is computed
-    // step 2: rows (s, a, b), new column r -- wanted iff r < s
+    // Wanted pairs (r, s), r < s or r <= s, numbered row-major: T3 is kept PACKED by pair, T3p[q, pair, a], so that
+    // step 4 is a dense GEMM over m * npairs rows (in the plain layout its 128-row tiles would span the whole
+    // range of s and none could be skipped).
+    std::vector<long long> host_tables((size_t)(M * M + M * (M + 1) / 2));
+    long long* slot_of_rs = host_tables.data();        // [r * M + s] -> pair * P, or -1 for an unwanted pair
+    long long* rs_of_pair = host_tables.data() + M * M;  // [pair] -> r * M + s
+    int64_t npairs = 0;
+    for (int64_t r = 0; r < M; ++r)
+        for (int64_t sI = 0; sI < M; ++sI) {
+            const bool wanted = strict ? r < sI : r <= sI;
+            slot_of_rs[r * M + sI] = wanted ? npairs * P : -1;
+            if (wanted) rs_of_pair[npairs++] = r * M + sI;
+        }
+    if (npairs == 0) return qs_mirror_fill(out, td, M, symmetry, stream);  // m = 1, antisymmetric: everything is zero
+    // pageable source: staged by the runtime before the call returns
+    QS_CUDA(cudaMemcpyAsync(tables, host_tables.data(), host_tables.size() * sizeof(long long), cudaMemcpyHostToDevice,
+                            static_cast<cudaStream_t>(stream)));
+    const long long* dev_slot_of_rs = tables;
+    const long long* dev_rs_of_pair = tables + M * M;
+    // step 2: rows (s, a, b), new column r -- tiles wanted iff they hold some r < s;  T2[r, s, a, b]
     const QsTileMask m2 = {1, strict, 1, 1, N * N, M};
-    // step 3: rows (r, s, a) -- wanted iff r < s
-    const QsTileMask m3 = {2, strict, M * N, M, N, M};
-    // step 4: rows (q, r, s) -- wanted iff r < s
-    const QsTileMask m4 = {2, strict, M, M, 1, M};
     if ((rc = masked_rotated_quarter(bufA, td, M * N * N, N, P, img2, c_dtype, M, bufB, N, P, &m2, lists, stream))) return rc;
-    if ((rc = masked_rotated_quarter(bufB, td, M * M * N, N, P, img3, c_dtype, M, bufA, N, P, &m3, lists, stream))) return rc;
-    if ((rc = masked_rotated_quarter(bufA, td, M * M * M, N, P, img3, c_dtype, M, out, M, M, &m4, lists, stream))) return rc;
+    // step 3: rows (r, s, a) -- tiles wanted iff they hold some r < s;  packed store T3p[q, pair(r, s), a]
+    const QsTileMask m3 = {2, strict, M * N, M, N, M};
+    if ((rc = qs_quarter_transform_masked(bufB, td, M * M * N, N, P, img3, c_dtype, M, bufA, N, 1, 0, 1, 0, npairs * P,
+                                          &m3, lists, dev_slot_of_rs, nullptr, stream)))
+        return rc;
+    // step 4: dense over rows (q, pair);  out[p, q, r, s] at p M^3 + q M^2 + (r M + s)(pair)
+    if ((rc = qs_quarter_transform_masked(bufA, td, M * npairs, N, P, img3, c_dtype, M, out, npairs, 0, M * M, 1, 0,
+                                          M * M * M, nullptr, nullptr, nullptr, dev_rs_of_pair, stream)))
+        return rc;
     return qs_mirror_fill(out, td, M, symmetry, stream);
 }
 

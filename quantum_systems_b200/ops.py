@@ -85,17 +85,20 @@ ANTISYMMETRIC_LAST_PAIR = 1  # u[p,q,r,s] = -u[p,q,s,r]
 PARTICLE_EXCHANGE = 2        # u[p,q,r,s] =  u[q,p,s,r]
 
 
-def two_body_symmetry(u):
+def two_body_symmetry(u, first_match=False):
     """Exact device-side test of the two symmetries the transform can exploit; returns a bit mask of
-    ``ANTISYMMETRIC_LAST_PAIR`` and ``PARTICLE_EXCHANGE``.  Reads ``u`` once, stops at the first counter-example,
-    synchronises the stream."""
+    ``ANTISYMMETRIC_LAST_PAIR`` and ``PARTICLE_EXCHANGE``.  Reads ``u`` once per test, stops at the first
+    counter-example, synchronises the stream.  ``first_match`` skips the second test when the first holds."""
     u = _device_tensor(u, "u")
     n = u.shape[0]
     if tuple(u.shape) != (n, n, n, n):
         raise ValueError(f"u must be (n,n,n,n), got {tuple(u.shape)}")
     flags = ctypes.c_int(0)
     scratch = torch.empty(2, dtype=torch.int32, device=u.device)
-    _native.call("qs_two_body_symmetry", _ptr(u), _code(u), n, ctypes.byref(flags), _ptr(scratch), _stream())
+    _native.call(
+        "qs_two_body_symmetry", _ptr(u), _code(u), n, int(bool(first_match)), ctypes.byref(flags), _ptr(scratch),
+        _stream(),
+    )
     return flags.value
 
 
@@ -114,7 +117,7 @@ def transform_two_body(u, C, C_tilde=None, symmetry=None):
     if symmetry is None:
         symmetry = 0
         if min(n, m) >= SYMMETRY_MIN_N:
-            flags = two_body_symmetry(u)
+            flags = two_body_symmetry(u, first_match=True)
             symmetry = (
                 ANTISYMMETRIC_LAST_PAIR if flags & ANTISYMMETRIC_LAST_PAIR
                 else PARTICLE_EXCHANGE if flags & PARTICLE_EXCHANGE else 0
