@@ -70,6 +70,18 @@ int qs_transform_two_body_symmetric(const void* u, int u_dtype, const void* C, c
                                     int c_dtype, int64_t n, int64_t n_new, int symmetry, void* out,
                                     void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Building blocks of the SHARDED symmetry-aware transform (anti-symmetric u only: its mirror image stays inside a
+ * (p, q) plane, i.e. on the rank that owns p).  Of each pair (r, s), (s, r) the rank that owns r computes the one
+ * whose cyclic distance (s - r) mod m is the shorter (qs_cyclic_pair_wanted; ties go to r < s), so every r has the
+ * same number of partners and the contiguous r-partition stays balanced.
+ *   qs_is_antisymmetric_last_pair : exact test on a rank's slab of `planes` leading-index planes (the caller
+ *                                   combines the ranks' flags).
+ *   qs_cyclic_antisymmetric_fill  : out[p,q,r,s] = -out[p,q,s,r] for the pairs not computed, zero diagonal. */
+int qs_is_antisymmetric_last_pair(const void* u, int dtype, int64_t n, int64_t planes, int* host_flag,
+                                  void* device_scratch, void* stream);
+int qs_cyclic_antisymmetric_fill(void* out, int dtype, int64_t m, int64_t planes, void* stream);
+int qs_cyclic_pair_wanted(int64_t r, int64_t s, int64_t m);
+
 /* ---------------------------------------------------------------------------------------------
  * One quarter step, exposed for the sharded (multi-GPU) schedule and for the grid Coulomb build.
  *
@@ -126,6 +138,27 @@ int qs_transform_two_body_diagonal_workspace_bytes(int64_t n, int64_t m, int w_d
 int qs_transform_two_body_diagonal(const void* w2d, int w_dtype, const void* C, const void* Ct,
                                    int c_dtype, int64_t n, int64_t m, int anti_symmetrize, void* out,
                                    void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Quarter steps with TABULATED row placement (packed pair layouts of the symmetry-aware transforms).
+ * Rows are split x = xq * x_inner + xr.
+ *   qs_quarter_transform_rows         : row x is stored at xq_table[xq] + xr * sx0 (+ the column term of
+ *       qs_quarter_transform); a NEGATIVE table entry drops the rows of that xq, and CTA tiles without any kept row
+ *       are not launched at all (the tile list is derived from host_xq_table, the host copy of the device table
+ *       xq_table; list_ws: qs_quarter_tile_list_bytes() bytes of device memory).
+ *   qs_quarter_transform_scatter_rows : the scattering store with row x at xq * sx1 + xr_table[xr] inside the
+ *       destination buffer chosen by the column (see qs_quarter_transform_scatter).
+ * Tables are int64 element offsets in device memory. */
+int qs_quarter_tile_list_bytes(int64_t X, int64_t K, int64_t W, int a_dtype, int m_dtype, int64_t* bytes);
+int qs_quarter_transform_rows(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda,
+                              const void* image, int m_dtype, int64_t W, void* out, int64_t x_inner,
+                              int64_t sx0, const int64_t* host_xq_table, const int64_t* xq_table,
+                              int64_t w_inner, int64_t sw0, int64_t sw1, void* list_ws,
+                              int64_t list_ws_bytes, void* stream);
+int qs_quarter_transform_scatter_rows(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda,
+                                      const void* image, int m_dtype, int64_t W,
+                                      void* const* host_out_table, int64_t n_dest, int64_t x_inner,
+                                      int64_t sx1, const int64_t* xr_table, int64_t w_inner,
+                                      int64_t sw0, int64_t w_deal, void* stream);
 
 /* Copy `rows` rows of n elements into rows of `pitch` >= n elements, zero-filling the tail (real
  * tensors with odd n need an even pitch before they can be described to TMA). */

@@ -976,7 +976,8 @@ int quarter_launch(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda
                    int64_t W, void* out, void* const* out_table, int64_t n_dest, int64_t x_inner, int64_t x_mid,
                    int64_t sx0, int64_t sx1, int64_t sx2, int64_t w_inner, int64_t sw0, int64_t sw1, int64_t w_deal,
                    void* stream, const QsTileMask* mask = nullptr, void* list_ws = nullptr,
-                   const long long* xq_table = nullptr, const long long* xr_table = nullptr) {
+                   const long long* xq_table = nullptr, const long long* xr_table = nullptr,
+                   const long long* host_xq_table = nullptr) {
     QS_REQUIRE(A && image && (out || out_table), "qs_quarter_transform: null pointer");
     QS_REQUIRE(w_deal >= 1 && w_deal < (W > 1 ? W : 2) && gcd64(w_deal, W) == 1,
                "qs_quarter_transform_scatter: the dealing multiplier %lld is not coprime to W = %lld",
@@ -1030,9 +1031,11 @@ int quarter_launch(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda
     // symmetry mask: per tile group, the ascending list of wanted linear tile ids, staged into list_ws
     std::vector<uint32_t> lists[2];
     double wanted_fraction = 1.0;
-    QS_REQUIRE(!(xq_table || xr_table) || n_dest == 0, "internal: row-offset tables and scattering do not combine");
-    if (mask && mask->kind) {
-        QS_REQUIRE(list_ws && w_deal == 1 && n_dest == 0, "internal: a masked quarter transform needs list space");
+    QS_REQUIRE(!(xq_table || xr_table) || x_mid == 0xFFFFFFFFLL,
+               "qs_quarter_transform: row-offset tables need the two-level row split");
+    const bool masked = (mask && mask->kind) || host_xq_table;
+    if (masked) {
+        QS_REQUIRE(list_ws && w_deal == 1 && n_dest == 0, "qs_quarter_transform: a masked launch needs list space");
         const int64_t tiles_x = qs_ceil_div(X, kBlockX);
         const int cols_per_elem = (out_complex && !tl.split) ? 2 : 1;  // real columns per output element
         int64_t all = 0, kept = 0;
@@ -1045,7 +1048,15 @@ int quarter_launch(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda
                     int64_t c1 = c0 + 8 * gr.NT - 1;
                     if (c1 > tl.Wp - 1) c1 = tl.Wp - 1;
                     ++all;
-                    if (tile_wanted(*mask, x0, x1, c0 / cols_per_elem, c1 / cols_per_elem)) {
+                    bool wanted;
+                    if (host_xq_table) {
+                        // rows whose table entry is negative are dropped: a tile is wanted iff one of its rows is kept
+                        wanted = false;
+                        for (int64_t xq = x0 / x_inner; xq <= x1 / x_inner && !wanted; ++xq) wanted = host_xq_table[xq] >= 0;
+                    } else {
+                        wanted = tile_wanted(*mask, x0, x1, c0 / cols_per_elem, c1 / cols_per_elem);
+                    }
+                    if (wanted) {
                         lists[gi].push_back((uint32_t)(rt * gr.tiles_w + ct));
                         ++kept;
                     }
@@ -1062,7 +1073,7 @@ int quarter_launch(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda
         const TileGroup& gr = tl.group[gi];
         QuarterParams p;
         memset(&p, 0, sizeof(p));
-        if (mask && mask->kind) {
+        if (masked) {
             if (lists[gi].empty()) continue;
             // pageable source: the runtime stages the bytes before returning
             QS_CUDA(cudaMemcpyAsync(list_dev, lists[gi].data(), lists[gi].size() * sizeof(uint32_t),
@@ -1122,6 +1133,37 @@ int qs_quarter_transform_masked(const void* A, int a_dtype, int64_t X, int64_t K
                                 const long long* xq_table, const long long* xr_table, void* stream) {
     return quarter_launch(A, a_dtype, X, K, lda, image, m_dtype, W, out, nullptr, 0, x_inner, 0xFFFFFFFFLL, sx0, sx1, 0,
                           w_inner, sw0, sw1, 1, stream, mask, list_ws, xq_table, xr_table);
+}
+
+extern "C" int qs_quarter_tile_list_bytes(int64_t X, int64_t K, int64_t W, int a_dtype, int m_dtype, int64_t* bytes) {
+    QS_REQUIRE(X > 0 && K > 0 && W > 0 && bytes, "qs_quarter_tile_list_bytes: bad arguments");
+    *bytes = qs_tile_list_bytes(X, K, W, a_dtype, m_dtype);
+    return QS_OK;
+}
+
+extern "C" int qs_quarter_transform_rows(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda,
+                                         const void* image, int m_dtype, int64_t W, void* out, int64_t x_inner,
+                                         int64_t sx0, const int64_t* host_xq_table, const int64_t* xq_table,
+                                         int64_t w_inner, int64_t sw0, int64_t sw1, void* list_ws,
+                                         int64_t list_ws_bytes, void* stream) {
+    QS_REQUIRE(host_xq_table && xq_table && list_ws, "qs_quarter_transform_rows: null pointer");
+    QS_REQUIRE(X > 0 && K > 0 && W > 0 && list_ws_bytes >= qs_tile_list_bytes(X, K, W, a_dtype, m_dtype),
+               "qs_quarter_transform_rows: tile-list space too small");
+    return quarter_launch(A, a_dtype, X, K, lda, image, m_dtype, W, out, nullptr, 0, x_inner, 0xFFFFFFFFLL, sx0, 0, 0,
+                          w_inner, sw0, sw1, 1, stream, nullptr, list_ws,
+                          reinterpret_cast<const long long*>(xq_table), nullptr,
+                          reinterpret_cast<const long long*>(host_xq_table));
+}
+
+extern "C" int qs_quarter_transform_scatter_rows(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda,
+                                                 const void* image, int m_dtype, int64_t W,
+                                                 void* const* host_out_table, int64_t n_dest, int64_t x_inner,
+                                                 int64_t sx1, const int64_t* xr_table, int64_t w_inner, int64_t sw0,
+                                                 int64_t w_deal, void* stream) {
+    QS_REQUIRE(host_out_table && n_dest > 0 && xr_table, "qs_quarter_transform_scatter_rows: null pointer");
+    return quarter_launch(A, a_dtype, X, K, lda, image, m_dtype, W, nullptr, host_out_table, n_dest, x_inner,
+                          0xFFFFFFFFLL, 0, sx1, 0, w_inner, sw0, 0, w_deal, stream, nullptr, nullptr, nullptr,
+                          reinterpret_cast<const long long*>(xr_table));
 }
 
 extern "C" int qs_quarter_transform(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda, const void* image,

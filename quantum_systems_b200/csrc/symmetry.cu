@@ -144,7 +144,92 @@ __global__ void __launch_bounds__(256) mirror_fill_kernel(double* __restrict__ o
     }
 }
 
+// Which of the two ordered pairs (r, s), (s, r) the SHARDED symmetry-aware transform computes: the one whose
+// cyclic distance d = (s - r) mod m is the shorter (ties, 2 d = m, go to r < s).  Every r then has the same number
+// of partners s, so the contiguous r-partition of the ranks stays balanced (r < s would give rank 0 fifteen times
+// the pairs of rank 7).
+__host__ __device__ __forceinline__ bool cyclic_wanted(int r, int s, int m) {
+    const int d = s >= r ? s - r : s - r + m;
+    return d > 0 && (2 * d < m || (2 * d == m && r < s));
+}
+
+// out[p,q,r,s] = -out[p,q,s,r] for every pair the cyclic rule did not compute, out[p,q,r,r] = 0.
+// grid (tiles * tiles, m, planes): the block owns target tile (tr, ts) and reads source tile (ts, tr).
+template <bool COMPLEX>
+__global__ void __launch_bounds__(256) cyclic_fill_kernel(double* __restrict__ out, int n, int tiles) {
+    const int tr = blockIdx.x / tiles, ts = blockIdx.x % tiles;
+    __shared__ double vre[kTile][kTile + 1], vim[COMPLEX ? kTile : 1][kTile + 1];
+    const int r0 = tr * kTile, s0 = ts * kTile;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const long long plane = ((long long)blockIdx.z * n + blockIdx.y) * n * n;
+    for (int i = ty; i < kTile; i += 8)
+        if (s0 + i < n && r0 + tx < n) {
+            const Val<COMPLEX> v = Val<COMPLEX>::load(out, plane + (long long)(s0 + i) * n + r0 + tx);
+            vre[i][tx] = v.re;
+            if (COMPLEX) vim[i][tx] = v.im;
+        }
+    __syncthreads();
+    for (int i = ty; i < kTile; i += 8) {
+        const int r = r0 + i, s = s0 + tx;
+        if (r >= n || s >= n || cyclic_wanted(r, s, n)) continue;
+        const long long at = plane + (long long)r * n + s;
+        const double re = r == s ? 0.0 : -vre[tx][i], im = (COMPLEX && r != s) ? -vim[tx][i] : 0.0;
+        if (COMPLEX) reinterpret_cast<double2*>(out)[at] = make_double2(re, im);
+        else out[at] = re;
+    }
+}
+
 }  // namespace
+
+// Exact test of u[p,q,r,s] == -u[p,q,s,r] on a leading-index slab of `planes` planes (a rank's shard).
+extern "C" int qs_is_antisymmetric_last_pair(const void* u, int dtype, int64_t n, int64_t planes, int* host_flag,
+                                             void* device_scratch, void* stream) {
+    QS_REQUIRE(host_flag && device_scratch && n > 0 && n <= 65535 && planes >= 0, "qs_is_antisymmetric_last_pair: bad arguments");
+    QS_REQUIRE(dtype == QS_F64 || dtype == QS_C128, "qs_is_antisymmetric_last_pair: bad dtype");
+    *host_flag = 1;
+    if (planes == 0) return QS_OK;
+    QS_REQUIRE(u, "qs_is_antisymmetric_last_pair: null tensor");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int* ok = static_cast<int*>(device_scratch);
+    const int tiles = (int)qs_ceil_div(n, kTile);
+    int one = 1;
+    QS_CUDA(cudaMemcpyAsync(ok, &one, sizeof(int), cudaMemcpyHostToDevice, st));
+    const long long items = planes * n * (tiles * (tiles + 1) / 2);
+    const long long resident = (long long)qs_sm_count() * 8;
+    const unsigned grid = (unsigned)(items < resident ? items : resident);
+    const dim3 block(32, 8);
+    if (dtype == QS_C128)
+        symmetry_check_kernel<true, 1><<<grid, block, 0, st>>>(static_cast<const double*>(u), (int)n, tiles, items, ok);
+    else
+        symmetry_check_kernel<false, 1><<<grid, block, 0, st>>>(static_cast<const double*>(u), (int)n, tiles, items, ok);
+    QS_LAUNCH_CHECK();
+    QS_CUDA(cudaMemcpyAsync(&one, ok, sizeof(int), cudaMemcpyDeviceToHost, st));
+    QS_CUDA(cudaStreamSynchronize(st));
+    *host_flag = one ? 1 : 0;
+    return QS_OK;
+}
+
+// Complete `planes` planes of an (.., m, m, m) result of which only the pairs chosen by the cyclic rule were computed.
+extern "C" int qs_cyclic_antisymmetric_fill(void* out, int dtype, int64_t m, int64_t planes, void* stream) {
+    QS_REQUIRE(m > 0 && m <= 32767 && planes >= 0 && planes <= 65535, "qs_cyclic_antisymmetric_fill: bad arguments");
+    QS_REQUIRE(dtype == QS_F64 || dtype == QS_C128, "qs_cyclic_antisymmetric_fill: bad dtype");
+    if (planes == 0) return QS_OK;
+    QS_REQUIRE(out, "qs_cyclic_antisymmetric_fill: null tensor");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int tiles = (int)qs_ceil_div(m, kTile);
+    const dim3 block(32, 8);
+    const dim3 grid((unsigned)(tiles * tiles), (unsigned)m, (unsigned)planes);
+    int span = -1;
+    qs_timing_begin(QS_FAMILY_SPIN_PASS, 1.5 * (double)planes * m * m * m * 8.0 * qs_elem_doubles(dtype), stream, &span);
+    if (dtype == QS_C128) cyclic_fill_kernel<true><<<grid, block, 0, st>>>(static_cast<double*>(out), (int)m, tiles);
+    else cyclic_fill_kernel<false><<<grid, block, 0, st>>>(static_cast<double*>(out), (int)m, tiles);
+    QS_LAUNCH_CHECK();
+    qs_timing_end(span, stream);
+    return QS_OK;
+}
+
+// Host helper: 1 if the cyclic rule computes the ordered pair (r, s) of an extent-m index pair.
+extern "C" int qs_cyclic_pair_wanted(int64_t r, int64_t s, int64_t m) { return cyclic_wanted((int)r, (int)s, (int)m) ? 1 : 0; }
 
 extern "C" int qs_two_body_symmetry(const void* u, int dtype, int64_t n, int first_match, int* host_flags,
                                     void* device_scratch, void* stream) {

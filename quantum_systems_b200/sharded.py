@@ -44,6 +44,18 @@ def block_partition(n, world):
     return block, [min(r * block, n) for r in range(world + 1)]
 
 
+# below this extent the symmetry test costs more than the tiles it saves
+SYMMETRY_MIN_N = 48
+
+
+def cyclic_wanted(r, s, m):
+    """Which of the ordered pairs (r, s), (s, r) the sharded symmetry-aware transform computes: the one whose
+    cyclic distance ``(s - r) mod m`` is the shorter; ties (``2 d = m``) go to ``r < s``.  Same rule as
+    ``qs_cyclic_pair_wanted`` (csrc/symmetry.cu); works on numpy index arrays."""
+    d = (s - r) % m
+    return (d > 0) & ((2 * d < m) | ((2 * d == m) & (r < s)))
+
+
 def padded_pitch(n, dtype):
     """Row pitch (elements) of a contracted axis of extent n: real rows must be a multiple of 16 bytes
     to be described to TMA (csrc/transform.cu)."""
@@ -123,6 +135,49 @@ class CudaEngine:
             "qs_quarter_transform", ctypes.c_void_p(A.at(0)), _CODES[A.dtype], X, K, lda,
             ctypes.c_void_p(image.data_ptr()), _CODES[m_dtype], W, ctypes.c_void_p(out.at(out_offset)), x_inner, sx0,
             sx1, w_inner, sw0, sw1, self._stream(),
+        )
+
+    # symmetry-aware steps (csrc/symmetry.cu, tabulated row placement of csrc/quarter_gemm.cu)
+    def index_table(self, host_int64):
+        return torch.from_numpy(host_int64).cuda()
+
+    def is_antisymmetric(self, buf, n, planes):
+        flag = ctypes.c_int(1)
+        scratch = torch.empty(2, dtype=torch.int32, device="cuda")
+        _native.call(
+            "qs_is_antisymmetric_last_pair", ctypes.c_void_p(buf.at(0)), _CODES[buf.dtype], n, planes,
+            ctypes.byref(flag), ctypes.c_void_p(scratch.data_ptr()), self._stream(),
+        )
+        return bool(flag.value)
+
+    def cyclic_fill(self, buf, m, planes):
+        _native.call("qs_cyclic_antisymmetric_fill", ctypes.c_void_p(buf.at(0)), _CODES[buf.dtype], m, planes,
+                     self._stream())
+
+    def quarter_rows(self, A, X, K, lda, image, m_dtype, W, out, x_inner, sx0, host_table, dev_table, w_inner, sw0,
+                     sw1):
+        if X <= 0:
+            return
+        nbytes = ctypes.c_int64(0)
+        _native.call("qs_quarter_tile_list_bytes", X, K, W, _CODES[A.dtype], _CODES[m_dtype], ctypes.byref(nbytes))
+        lists = torch.empty(nbytes.value, dtype=torch.uint8, device="cuda")
+        _native.call(
+            "qs_quarter_transform_rows", ctypes.c_void_p(A.at(0)), _CODES[A.dtype], X, K, lda,
+            ctypes.c_void_p(image.data_ptr()), _CODES[m_dtype], W, ctypes.c_void_p(out.at(0)), x_inner, sx0,
+            ctypes.c_void_p(host_table.ctypes.data), ctypes.c_void_p(dev_table.data_ptr()), w_inner, sw0, sw1,
+            ctypes.c_void_p(lists.data_ptr()), nbytes.value, self._stream(),
+        )
+        lists.record_stream(torch.cuda.current_stream())
+
+    def quarter_scatter_rows(self, A, X, K, lda, image, m_dtype, W, dests, x_inner, sx1, xr_table, w_inner, sw0,
+                             deal=1):
+        if X <= 0:
+            return
+        table = (ctypes.c_void_p * len(dests))(*[buf.at(off) for buf, off in dests])
+        _native.call(
+            "qs_quarter_transform_scatter_rows", ctypes.c_void_p(A.at(0)), _CODES[A.dtype], X, K, lda,
+            ctypes.c_void_p(image.data_ptr()), _CODES[m_dtype], W, table, len(dests), x_inner, sx1,
+            ctypes.c_void_p(xr_table.data_ptr()), w_inner, sw0, int(deal), self._stream(),
         )
 
     # consumers of a shard (csrc/consumers.cu)
@@ -526,6 +581,41 @@ class _RankTransform:
         eng.quarter_scatter(self.scratch, m * R * m, n, P, self.img4_scatter, self.c_dtype, m, dests, m, R, 1, m, m * m,
                             self.r_block, m**3, deal=self.deal)
 
+    # ---- anti-symmetric u: steps 3 and 4 on half of the (r, s) pairs (cyclic rule), packed by pair -------------
+    def prepare_pairs(self):
+        """Pair tables of this rank: for every owned r the partners s the cyclic rule assigns to (r, s)."""
+        import numpy
+
+        m, R, P = self.m, self.R, self.P
+        r = self.r_off[self.rank] + numpy.arange(R, dtype=numpy.int64)[:, None]
+        sI = numpy.arange(m, dtype=numpy.int64)[None, :]
+        wanted = cyclic_wanted(r, sI, m)
+        self.npairs = int(wanted.sum())
+        slot = numpy.full((R, m), -1, dtype=numpy.int64)
+        slot[wanted] = numpy.arange(self.npairs, dtype=numpy.int64) * P  # row-major (r_loc, s) order
+        self.slot_of_rs = numpy.ascontiguousarray(slot.reshape(-1))
+        self.rs_of_pair = numpy.ascontiguousarray((r * m + sI)[wanted])
+        if self.npairs:
+            self.slot_of_rs_dev = self.engine.index_table(self.slot_of_rs)
+            self.rs_of_pair_dev = self.engine.index_table(self.rs_of_pair)
+
+    def step3_pairs(self, recv_local):
+        """T3p[q, pair(r_loc, s), a] = sum_b T2[r_loc, s, a, b] C~[q, b] for the wanted pairs only."""
+        eng, n, m, R, P = self.engine, self.n, self.m, self.R, self.P
+        if self.npairs == 0:
+            return
+        eng.quarter_rows(recv_local, R * m * n, n, P, self.img3, self.c_dtype, m, self.scratch, n, 1, self.slot_of_rs,
+                         self.slot_of_rs_dev, 1, 0, self.npairs * P)
+
+    def step4_scatter_pairs(self, out):
+        """u'[p, q, r, s] = sum_a T3p[q, pair, a] C~[p, a] for the wanted pairs, stored into the rank that owns p."""
+        eng, n, m, P = self.engine, self.n, self.m, self.P
+        if self.npairs == 0:
+            return
+        dests = [(out[j], 0) for j in range(self.ctx.world)]
+        eng.quarter_scatter_rows(self.scratch, m * self.npairs, n, P, self.img4_scatter, self.c_dtype, m, dests,
+                                 self.npairs, m * m, self.rs_of_pair_dev, self.r_block, m**3, deal=self.deal)
+
     def step4_local(self, out_local):
         """Collective schedule: u'[p, q, r_loc, s] dense on this rank (sharded on the third index)."""
         eng, n, m, R, P = self.engine, self.n, self.m, self.R, self.P
@@ -539,17 +629,41 @@ def _slice(buf, offset, numel):
     return buf.slice(offset, numel)
 
 
-def transform_two_body_sharded(u, C, C_tilde=None):
+def is_antisymmetric_last_pair(u):
+    """Exact, collective test of ``u[p,q,r,s] == -u[p,q,s,r]`` on a ``ShardedTwoBody``: every rank tests its own
+    planes on the device (``qs_is_antisymmetric_last_pair``), the flags are combined with a one-element all-reduce."""
+    ctx = u.ctx
+    ok = True
+    for r in ctx.local_ranks:
+        p0, p1 = u.planes(r)
+        ok = ok and ctx.engine.is_antisymmetric(u.buffers[r][r], u.n, p1 - p0)
+    if isinstance(ctx, ProcessContext) and ctx.world > 1:
+        flag = torch.tensor([1.0 if ok else 0.0], dtype=torch.float32, device="cuda" if ctx.on_cuda else "cpu")
+        ctx.dist.all_reduce(flag, op=ctx.dist.ReduceOp.MIN, group=ctx.group)
+        ok = bool(flag.item() > 0.5)
+    return ok
+
+
+def transform_two_body_sharded(u, C, C_tilde=None, symmetry=None):
     """Four-index transform of a ``ShardedTwoBody``; returns a new handle sharded on the leading index.
 
     Same contraction order (s, r, q, p) and operands as the single-GPU ``ops.transform_two_body``
     (reference basis_set.py:336-350).  Rectangular ``C`` (n, m) changes the extent; ``C_tilde`` (m, n)
     defaults to ``C^dagger``.
+
+    ``symmetry=None``: in the peer schedule an exactly anti-symmetric ``u`` (``u_pqrs = -u_pqsr``, tested on the
+    device) runs steps 3 and 4 on half of the (r, s) pairs -- of (r, s) and (s, r) the rank owning r computes the
+    one at the shorter cyclic distance, so the ranks stay balanced -- and every rank completes its own planes with
+    the mirror image (no extra communication).  ``symmetry=0`` forces the four full steps.
     """
     ctx = u.ctx
     n, m = C.shape
     if n != u.n:
         raise ValueError(f"C has {n} rows but u has {u.n} orbitals")
+    if symmetry is None:
+        symmetry = 1 if (ctx.exchange == "peer" and min(n, m) >= SYMMETRY_MIN_N and is_antisymmetric_last_pair(u)) else 0
+    if symmetry and ctx.exchange != "peer":
+        raise ValueError("the symmetry-aware sharded transform needs the peer exchange")
     work = {r: _RankTransform(ctx, r, n, m, u.dtype, C.dtype) for r in ctx.local_ranks}
     t_dtype = next(iter(work.values())).t_dtype
     for w in work.values():
@@ -569,9 +683,17 @@ def transform_two_body_sharded(u, C, C_tilde=None):
             w.step2_scatter(recv[r])
         ctx.barrier()  # all tiles of T2 have landed
         for r, w in work.items():
-            w.step3(recv[r][r])
-            w.step4_scatter(out[r])
+            if symmetry:
+                w.prepare_pairs()
+                w.step3_pairs(recv[r][r])
+                w.step4_scatter_pairs(out[r])
+            else:
+                w.step3(recv[r][r])
+                w.step4_scatter(out[r])
         ctx.barrier()  # all tiles of u' have landed
+        if symmetry:
+            for r, w in work.items():
+                ctx.engine.cyclic_fill(out[r][r], m, w.R)  # the other half of every local plane: -u'[p,q,s,r]
         spare = u.buffers if (u.dtype == t_dtype and m == n) else None
         return ShardedTwoBody(ctx, m, t_dtype, out, spare)
 

@@ -38,6 +38,19 @@ def main():
                 expected2 = oracle.transform_two_body_elements(expected, C)
                 full = out2.gather().cpu().numpy()
                 assert np.abs(full - expected2).max() <= 1e-11 * np.abs(expected2).max()
+        # anti-symmetric input above the detection threshold: the symmetry-aware schedule over real peer memory
+        n = 48
+        rng = np.random.default_rng(48)
+        u = rng.standard_normal((n,) * 4)
+        u = u - u.transpose(0, 1, 3, 2)
+        C = np.linalg.qr(rng.standard_normal((n, n)))[0]
+        basis = sharded.ShardedBasisSet.from_global(ctx, np.eye(n), np.eye(n), u)
+        assert sharded.is_antisymmetric_last_pair(basis.u)
+        out = sharded.transform_two_body_sharded(basis.u, torch.from_numpy(C).cuda())
+        expected = oracle.transform_two_body_elements(u, C)
+        full = out.gather().cpu().numpy()
+        assert np.abs(full - expected).max() <= 1e-12 * np.abs(expected).max()
+        assert np.array_equal(full, -full.transpose(0, 1, 3, 2))
         # spin doubling + change_basis + Fock through the container
         rng = np.random.default_rng(5)
         l, n_occ = 8, 4

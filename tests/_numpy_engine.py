@@ -115,3 +115,51 @@ class NumpyEngine:
                 direct += slab[i - p0, j, i, j]
                 exchange += slab[i - p0, j, j, i]
         return torch.tensor([tr_h, direct, exchange], dtype=torch.complex128)
+
+    # symmetry-aware steps: documented semantics of qs_quarter_transform_rows / _scatter_rows /
+    # qs_is_antisymmetric_last_pair / qs_cyclic_antisymmetric_fill
+    def index_table(self, host_int64):
+        return torch.from_numpy(host_int64)
+
+    def is_antisymmetric(self, buf, n, planes):
+        slab = buf.flat()[: planes * n**3].reshape(planes, n, n, n)
+        return bool(np.array_equal(slab, -slab.transpose(0, 1, 3, 2)))
+
+    def cyclic_fill(self, buf, m, planes):
+        from quantum_systems_b200.sharded import cyclic_wanted
+
+        slab = buf.flat()[: planes * m**3].reshape(planes, m, m, m)
+        r, s = np.arange(m)[:, None], np.arange(m)[None, :]
+        wanted = cyclic_wanted(r, s, m)
+        mirrored = -slab.transpose(0, 1, 3, 2)
+        slab[...] = np.where(wanted, slab, np.where(r == s, 0, mirrored))
+
+    def quarter_rows(self, A, X, K, lda, image, m_dtype, W, out, x_inner, sx0, host_table, dev_table, w_inner, sw0, sw1):
+        if X <= 0:
+            return
+        res = self._product(A, X, K, lda, image)
+        x = np.arange(X)
+        base = host_table[x // x_inner]
+        keep = base >= 0
+        ax = base[keep] + (x[keep] % x_inner) * sx0
+        w = np.arange(W)
+        aw = (w // w_inner) * sw1 + (w % w_inner) * sw0
+        out.flat()[ax[:, None] + aw[None, :]] = res[keep]
+
+    def quarter_scatter_rows(self, A, X, K, lda, image, m_dtype, W, dests, x_inner, sx1, xr_table, w_inner, sw0, deal=1):
+        if X <= 0:
+            return
+        res = self._product(A, X, K, lda, image)
+        if deal > 1:
+            physical = np.empty_like(res)
+            physical[:, (np.arange(W) * deal) % W] = res
+            res = physical
+        table = xr_table.numpy() if isinstance(xr_table, torch.Tensor) else np.asarray(xr_table)
+        x = np.arange(X)
+        ax = (x // x_inner) * sx1 + table[x % x_inner]
+        for j, (buf, off) in enumerate(dests):
+            cols = np.arange(j * w_inner, min((j + 1) * w_inner, W))
+            if len(cols) == 0:
+                continue
+            aw = (cols % w_inner) * sw0
+            buf.flat()[off + ax[:, None] + aw[None, :]] = res[:, cols]

@@ -125,6 +125,43 @@ def test_emulated_consumers_of_a_sharded_tensor(world, complex_):
             basis.u.axpby_(1j)
 
 
+@pytest.mark.parametrize("world", [1, 2, 3, 4])
+@pytest.mark.parametrize("n,m,complex_", [(8, 8, False), (9, 9, False), (7, 10, True), (10, 6, True), (16, 16, False)])
+def test_emulated_symmetry_aware_schedule(world, n, m, complex_, monkeypatch):
+    """Anti-symmetric u: steps 3-4 on the pairs the cyclic rule selects (balanced over the r-partition), packed by
+    pair, local mirror fill -- against the oracle's four full steps; the result is exactly anti-symmetric."""
+    from quantum_systems_b200 import sharded
+
+    monkeypatch.setattr(sharded, "SYMMETRY_MIN_N", 4)
+    rng = np.random.default_rng(10 * n + m + world)
+    u = rand(rng, (n,) * 4, complex_)
+    u = u - u.transpose(0, 1, 3, 2)
+    C = rand(rng, (n, m), complex_)
+    ctx = sharded.EmulatedContext(world, engine=NumpyEngine())
+    basis = sharded.ShardedBasisSet.from_global(ctx, np.eye(n), np.eye(n), u)
+    assert sharded.is_antisymmetric_last_pair(basis.u)
+    out = sharded.transform_two_body_sharded(basis.u, torch.from_numpy(C))
+    expected = oracle.transform_two_body_elements(u, C)
+    got = out.gather().numpy()
+    np.testing.assert_allclose(got, expected, rtol=1e-12, atol=1e-12 * np.abs(expected).max())
+    np.testing.assert_array_equal(got, -got.transpose(0, 1, 3, 2))
+    # a tensor without the symmetry takes the four full steps
+    basis2 = sharded.ShardedBasisSet.from_global(ctx, np.eye(n), np.eye(n), u + 1.0)
+    assert not sharded.is_antisymmetric_last_pair(basis2.u)
+
+
+def test_cyclic_rule_picks_each_pair_once_and_balances_r():
+    from quantum_systems_b200.sharded import cyclic_wanted
+
+    for m in (1, 2, 3, 8, 9, 50, 400):
+        r, s = np.arange(m)[:, None], np.arange(m)[None, :]
+        w = cyclic_wanted(r, s, m)
+        assert not w.diagonal().any()
+        assert np.array_equal(w ^ w.T, ~np.eye(m, dtype=bool))  # exactly one of (r, s), (s, r)
+        per_r = w.sum(axis=1)
+        assert per_r.max() - per_r.min() <= 1  # every r has the same number of partners (+-1 for even m)
+
+
 def _free_port():
     with socket.socket() as sock:
         sock.bind(("127.0.0.1", 0))
