@@ -17,6 +17,10 @@ handles), for stream-ordered barriers and for the tiny all-gather of the Fock ma
 carries tensor data on this path.  ``exchange="collective"`` selects the plain
 ``all_to_all_single`` schedule instead (validation, and CPU/gloo tests of the partition logic).
 
+An exactly anti-symmetric ``u`` (every spin-doubled, anti-symmetrised tensor) is detected on the device and
+transformed with steps 3-4 on half of the (r, s) pairs (``cyclic_wanted`` keeps the ranks balanced); see
+``transform_two_body_sharded`` and DESIGN.md section 4.9.
+
 One process per GPU drives one rank (``ProcessContext``).  ``EmulatedContext`` drives all W ranks
 from one process on one device; it exists to test the schedule and the scattering kernel on a
 single GPU.
