@@ -404,8 +404,11 @@ def run_ours(args):
     if os.path.exists(prof):
         with open(prof) as fh:
             traffic = json.load(fh).get(f"n{n}", {}).get("dram_bytes_per_launch")
+    # share of the four full quarter steps that was actually issued (1.0 without symmetry; the tiny one-body
+    # launches of h and s are timed too but carry ~1e-4 of the flops)
     full_step_flops = 2.0 * n**5 / max(world, 1)
-    issued_share = (k_work.value / max(int(k_spans.value), 1)) / full_step_flops if k_spans.value else 1.0
+    issued_share = (k_work.value / args.steps) / (4.0 * full_step_flops) if k_work.value else 1.0
+    step_bytes = 4.0 * 2.0 * 8 * n**4 / max(world, 1) * issued_share  # read A once, write the result once, per step
     roofline = {
         "kernel": "quarter_gemm_kernel (FP64 DMMA.8x8x4 + TMA)",
         "bound": "tensor",
@@ -418,11 +421,11 @@ def run_ours(args):
         "(qs_probe_dmma_tflops); MEASURED_PEAKS.json holds only bf16 and HBM-copy figures",
         "launches_timed": int(k_spans.value),
         "kernel_share_of_step": k_ms.value / ms if ms > 0 else None,
-        "algorithmic_flops_per_launch": k_work.value / max(int(k_spans.value), 1),
+        # per quarter step of u (four per change_basis); the one-body launches of h and s are negligible
+        "algorithmic_flops_per_launch": k_work.value / (4.0 * args.steps),
         # one full quarter step reads 8 n^4 and writes 8 n^4 bytes; a masked step touches the issued share of it
-        "algorithmic_bytes_per_launch": 2.0 * 8 * n**4 * issued_share,
-        "hbm_gbs_at_achieved": (2.0 * 8 * n**4 * issued_share * int(k_spans.value)) / (k_ms.value * 1e-3) * 1e-9
-        if k_ms.value > 0 else None,
+        "algorithmic_bytes_per_launch": step_bytes / 4.0,
+        "hbm_gbs_at_achieved": step_bytes * args.steps / (k_ms.value * 1e-3) * 1e-9 if k_ms.value > 0 else None,
         "issued_share_of_full_steps": issued_share,
         "hbm_peak_gbs_measured": _measured_peaks().get("hbm_gbs"),
     }
