@@ -325,7 +325,10 @@ def run_ours(args):
             "mirror fill" if flags & 2 else "none found in the input"
         )
     else:
-        symmetry_note = "not exploited by the sharded schedule"
+        symmetry_note = (
+            "none: the synthetic planes of the sharded workload are independent random numbers (the sharded schedule "
+            "exploits exact anti-symmetry u_pqrs = -u_pqsr when it finds it, e.g. BASELINE configs[3] and [4])"
+        )
 
     # ---- leg 2: end to end through the public API with host arrays -------------------------------
     e2e = None
