@@ -149,6 +149,15 @@ int qs_transform_two_body_diagonal(const void* w2d, int w_dtype, const void* C, 
  *       destination buffer chosen by the column (see qs_quarter_transform_scatter).
  * Tables are int64 element offsets in device memory. */
 int qs_quarter_tile_list_bytes(int64_t X, int64_t K, int64_t W, int a_dtype, int m_dtype, int64_t* bytes);
+/* Host-only planning of a masked launch (no device is touched): the CTA tiles it would visit, as rows of
+ * (first row, last row, first output column, last output column) in host_tiles (capacity rows of 4 int64; may be
+ * NULL to only count).  Either a host row table (mask_kind = 0) or the analytic masks of the single-GPU
+ * symmetry-aware transform: kind 1 keeps tiles with some column < (<=) row_lo, kind 2 tiles with some row_hi < (<=)
+ * row_lo, where row_hi(x) = (x / dh) % mh and row_lo(x) = (x / dl) % ml. */
+int qs_quarter_plan_tiles(int64_t X, int64_t K, int64_t W, int a_dtype, int m_dtype, int64_t x_inner,
+                          int mask_kind, int strict, int64_t dh, int64_t mh, int64_t dl, int64_t ml,
+                          const int64_t* host_xq_table, int64_t* host_tiles, int64_t capacity,
+                          int64_t* count);
 int qs_quarter_transform_rows(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda,
                               const void* image, int m_dtype, int64_t W, void* out, int64_t x_inner,
                               int64_t sx0, const int64_t* host_xq_table, const int64_t* xq_table,

@@ -39,6 +39,7 @@ SIGNATURES = {
     "qs_is_antisymmetric_last_pair": [_ptr, _int, _i64, _i64, ctypes.POINTER(_int), _ptr, _ptr],
     "qs_cyclic_antisymmetric_fill": [_ptr, _int, _i64, _i64, _ptr],
     "qs_cyclic_pair_wanted": [_i64, _i64, _i64],
+    "qs_quarter_plan_tiles": [_i64, _i64, _i64, _int, _int, _i64, _int, _int, _i64, _i64, _i64, _i64, _ptr, _ptr, _i64, ctypes.POINTER(_i64)],
     "qs_quarter_tile_list_bytes": [_i64, _i64, _i64, _int, _int, ctypes.POINTER(_i64)],
     "qs_quarter_transform_rows": [_ptr, _int, _i64, _i64, _i64, _ptr, _int, _i64, _ptr, _i64, _i64, _ptr, _ptr, _i64, _i64, _i64, _ptr, _i64, _ptr],
     "qs_quarter_transform_scatter_rows": [_ptr, _int, _i64, _i64, _i64, _ptr, _int, _i64, ctypes.POINTER(_ptr), _i64, _i64, _i64, _ptr, _i64, _i64, _i64, _ptr],

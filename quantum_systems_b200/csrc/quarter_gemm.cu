@@ -972,6 +972,39 @@ bool tile_wanted(const QsTileMask& m, int64_t x0, int64_t x1, int64_t w0, int64_
     return m.strict ? hi < lo_max : hi <= lo_max;
 }
 
+// Per tile group, the ascending list of the linear tile ids (row_tile * tiles_w + col_tile) a masked launch visits:
+// by the row table (a tile is wanted iff one of its rows is kept) or by the analytic mask.  Returns the kept share.
+double plan_tile_lists(const Tiling& tl, int64_t X, int64_t x_inner, bool out_complex, const QsTileMask* mask,
+                       const long long* host_xq_table, std::vector<uint32_t> (&lists)[2]) {
+    const int64_t tiles_x = qs_ceil_div(X, kBlockX);
+    const int cols_per_elem = (out_complex && !tl.split) ? 2 : 1;  // real columns per output element
+    int64_t all = 0, kept = 0;
+    for (int gi = 0; gi < tl.ngroups; ++gi) {
+        const TileGroup& gr = tl.group[gi];
+        for (int64_t rt = 0; rt < tiles_x; ++rt) {
+            const int64_t x0 = rt * kBlockX, x1 = (x0 + kBlockX < X ? x0 + kBlockX : X) - 1;
+            for (int ct = 0; ct < gr.tiles_w; ++ct) {
+                const int64_t c0 = gr.w_first + (int64_t)ct * 8 * gr.NT;
+                int64_t c1 = c0 + 8 * gr.NT - 1;
+                if (c1 > tl.Wp - 1) c1 = tl.Wp - 1;
+                ++all;
+                bool wanted;
+                if (host_xq_table) {
+                    wanted = false;
+                    for (int64_t xq = x0 / x_inner; xq <= x1 / x_inner && !wanted; ++xq) wanted = host_xq_table[xq] >= 0;
+                } else {
+                    wanted = tile_wanted(*mask, x0, x1, c0 / cols_per_elem, c1 / cols_per_elem);
+                }
+                if (wanted) {
+                    lists[gi].push_back((uint32_t)(rt * gr.tiles_w + ct));
+                    ++kept;
+                }
+            }
+        }
+    }
+    return all ? (double)kept / (double)all : 1.0;
+}
+
 int quarter_launch(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda, const void* image, int m_dtype,
                    int64_t W, void* out, void* const* out_table, int64_t n_dest, int64_t x_inner, int64_t x_mid,
                    int64_t sx0, int64_t sx1, int64_t sx2, int64_t w_inner, int64_t sw0, int64_t sw1, int64_t w_deal,
@@ -1036,34 +1069,7 @@ int quarter_launch(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda
     const bool masked = (mask && mask->kind) || host_xq_table;
     if (masked) {
         QS_REQUIRE(list_ws && w_deal == 1 && n_dest == 0, "qs_quarter_transform: a masked launch needs list space");
-        const int64_t tiles_x = qs_ceil_div(X, kBlockX);
-        const int cols_per_elem = (out_complex && !tl.split) ? 2 : 1;  // real columns per output element
-        int64_t all = 0, kept = 0;
-        for (int gi = 0; gi < tl.ngroups; ++gi) {
-            const TileGroup& gr = tl.group[gi];
-            for (int64_t rt = 0; rt < tiles_x; ++rt) {
-                const int64_t x0 = rt * kBlockX, x1 = (x0 + kBlockX < X ? x0 + kBlockX : X) - 1;
-                for (int ct = 0; ct < gr.tiles_w; ++ct) {
-                    const int64_t c0 = gr.w_first + (int64_t)ct * 8 * gr.NT;
-                    int64_t c1 = c0 + 8 * gr.NT - 1;
-                    if (c1 > tl.Wp - 1) c1 = tl.Wp - 1;
-                    ++all;
-                    bool wanted;
-                    if (host_xq_table) {
-                        // rows whose table entry is negative are dropped: a tile is wanted iff one of its rows is kept
-                        wanted = false;
-                        for (int64_t xq = x0 / x_inner; xq <= x1 / x_inner && !wanted; ++xq) wanted = host_xq_table[xq] >= 0;
-                    } else {
-                        wanted = tile_wanted(*mask, x0, x1, c0 / cols_per_elem, c1 / cols_per_elem);
-                    }
-                    if (wanted) {
-                        lists[gi].push_back((uint32_t)(rt * gr.tiles_w + ct));
-                        ++kept;
-                    }
-                }
-            }
-        }
-        wanted_fraction = all ? (double)kept / (double)all : 1.0;
+        wanted_fraction = plan_tile_lists(tl, X, x_inner, out_complex, mask, host_xq_table, lists);
     }
     int span = -1;
     // issued flops; the split variant's Wp counts complex columns, each fed by Kp real multiply-adds per row
@@ -1133,6 +1139,42 @@ int qs_quarter_transform_masked(const void* A, int a_dtype, int64_t X, int64_t K
                                 const long long* xq_table, const long long* xr_table, void* stream) {
     return quarter_launch(A, a_dtype, X, K, lda, image, m_dtype, W, out, nullptr, 0, x_inner, 0xFFFFFFFFLL, sx0, sx1, 0,
                           w_inner, sw0, sw1, 1, stream, mask, list_ws, xq_table, xr_table);
+}
+
+// Host-only: the tiles a masked quarter transform would launch, as rows of (first row, last row, first output
+// column, last output column) -- for inspection and for CPU tests of the masks (no device is touched).
+// mask_kind 0 with a host_xq_table plans by the table; otherwise the analytic mask (kind, strict, dh, mh, dl, ml).
+extern "C" int qs_quarter_plan_tiles(int64_t X, int64_t K, int64_t W, int a_dtype, int m_dtype, int64_t x_inner,
+                                     int mask_kind, int strict, int64_t dh, int64_t mh, int64_t dl, int64_t ml,
+                                     const int64_t* host_xq_table, int64_t* host_tiles, int64_t capacity,
+                                     int64_t* count) {
+    QS_REQUIRE(X > 0 && K > 0 && W > 0 && x_inner > 0 && count, "qs_quarter_plan_tiles: bad arguments");
+    QS_REQUIRE(mask_kind || host_xq_table, "qs_quarter_plan_tiles: neither a mask nor a row table");
+    const Tiling tl = make_tiling(K, W, a_dtype, m_dtype);
+    const bool out_complex = a_dtype == QS_C128 || m_dtype == QS_C128;
+    const QsTileMask mask = {mask_kind, strict, dh, mh, dl, ml};
+    std::vector<uint32_t> lists[2];
+    plan_tile_lists(tl, X, x_inner, out_complex, &mask, reinterpret_cast<const long long*>(host_xq_table), lists);
+    const int cols_per_elem = (out_complex && !tl.split) ? 2 : 1;
+    int64_t n = 0;
+    for (int gi = 0; gi < tl.ngroups; ++gi) {
+        const TileGroup& gr = tl.group[gi];
+        for (uint32_t id : lists[gi]) {
+            if (host_tiles && n < capacity) {
+                const int64_t rt = id / gr.tiles_w, ct = id % gr.tiles_w;
+                const int64_t c0 = gr.w_first + ct * 8 * gr.NT;
+                int64_t c1 = c0 + 8 * gr.NT - 1;
+                if (c1 > tl.Wp - 1) c1 = tl.Wp - 1;
+                host_tiles[4 * n + 0] = rt * kBlockX;
+                host_tiles[4 * n + 1] = (rt * kBlockX + kBlockX < X ? rt * kBlockX + kBlockX : X) - 1;
+                host_tiles[4 * n + 2] = c0 / cols_per_elem;
+                host_tiles[4 * n + 3] = c1 / cols_per_elem;
+            }
+            ++n;
+        }
+    }
+    *count = n;
+    return QS_OK;
 }
 
 extern "C" int qs_quarter_tile_list_bytes(int64_t X, int64_t K, int64_t W, int a_dtype, int m_dtype, int64_t* bytes) {
