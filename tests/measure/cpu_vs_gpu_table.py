@@ -10,7 +10,7 @@ import time
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import qs_oracle as oracle  # noqa: E402  (CPU baseline / checker)
 from quantum_systems_b200 import ops  # noqa: E402
 
