@@ -330,6 +330,25 @@ def run_ours(args):
             "exploits exact anti-symmetry u_pqrs = -u_pqsr when it finds it, e.g. BASELINE configs[3] and [4])"
         )
 
+    # ---- leg 1b (one GPU): the same steps with the symmetry test switched off, i.e. the reference's four full
+    # quarter steps -- the number that is comparable with the sharded runs, whose synthetic planes carry no symmetry
+    value_full_steps = None
+    if world == 1:
+        ops.EXPLOIT_SYMMETRY = False
+        try:
+            for _ in range(max(args.warmup, 3)):
+                step()
+            torch.cuda.synchronize()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(args.steps):
+                step()
+            f1.record()
+            torch.cuda.synchronize()
+            value_full_steps = flops / (f0.elapsed_time(f1) / args.steps * 1e-3) * 1e-12
+        finally:
+            ops.EXPLOIT_SYMMETRY = True
+
     # ---- leg 2: end to end through the public API with host arrays -------------------------------
     e2e = None
     if not args.no_e2e and world == 1:
@@ -471,6 +490,7 @@ def run_ours(args):
             "l2": "inputs (8*n^4 bytes per tensor pass) exceed the 126 MB L2; no explicit flush",
             "symmetry": symmetry_note,
             "issued_flops_per_step": issued_flops_per_step,
+            "value_four_full_steps": value_full_steps,
         },
         "e2e": e2e,
         "gpu_launches": int(launches),

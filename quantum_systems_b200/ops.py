@@ -81,6 +81,8 @@ def real_coefficients_if_exact(u_is_complex, C, C_tilde):
 
 # below this extent the symmetry test costs more than the tiles it saves
 SYMMETRY_MIN_N = 48
+# False: `transform_two_body(symmetry=None)` never tests for symmetries and always runs the four full quarter steps
+EXPLOIT_SYMMETRY = True
 ANTISYMMETRIC_LAST_PAIR = 1  # u[p,q,r,s] = -u[p,q,s,r]
 PARTICLE_EXCHANGE = 2        # u[p,q,r,s] =  u[q,p,s,r]
 
@@ -116,7 +118,7 @@ def transform_two_body(u, C, C_tilde=None, symmetry=None):
         raise ValueError(f"u must have shape {(n,) * 4} to be contracted with C {tuple(C.shape)}, got {tuple(u.shape)}")
     if symmetry is None:
         symmetry = 0
-        if min(n, m) >= SYMMETRY_MIN_N:
+        if EXPLOIT_SYMMETRY and min(n, m) >= SYMMETRY_MIN_N:
             flags = two_body_symmetry(u, first_match=True)
             symmetry = (
                 ANTISYMMETRIC_LAST_PAIR if flags & ANTISYMMETRIC_LAST_PAIR
