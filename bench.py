@@ -3,23 +3,30 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-One *step* = one ``BasisSet.change_basis(C)`` pass over one synthetic basis set.
+One *step* = one ``change_basis(C)`` pass over one synthetic basis set.  The workload follows BASELINE.json:
 
-* N = 1: BASELINE.json ``configs[1]`` -- synthetic real FP64 ``BasisSet`` with l = 128, random
-  orthonormal C.
-* N > 1 (torchrun, one rank per GPU): ONE tensor sharded on its leading index across the ranks,
-  re-partitioned by one all-to-all between the second and third quarter transforms; n grows as
-  ``128 * N**(1/5)`` (148 / 168 / 192 at N = 2 / 4 / 8) so the flops per GPU stay fixed: weak scaling.
+* N = 1: ``configs[1]`` -- synthetic real FP64 ``BasisSet`` with l = 128, random orthonormal C.
+* N = 2, 4: ``configs[3]`` -- 256 spin-orbitals, complex128, bi-orthogonal ``change_basis(C, C_tilde = C^-1)``,
+  one tensor sharded over the N GPUs (one process per GPU).
+* N = 8: ``configs[4]`` -- ``GeneralOrbitalSystem`` from l = 200 spatial orbitals (400 spin-orbitals, 204.8 GB real
+  FP64 ``u``): sharded ODQD grid build -> add_spin + anti_symmetrize_u -> change_basis; ``configs[3]`` runs as a
+  second leg.
+* every N also runs the *weak series*: an anti-symmetrised real GOS tensor with n = 128 N^(1/5) spin-orbitals
+  (128 / 148 / 168 / 192: equal flops per GPU), the like-for-like series across N (``config.legs``).
 
-Printed JSON line (rank 0): ``value`` = whole-job TFLOP/s with inputs resident in HBM, device-timed
-with CUDA events (max over ranks); ``e2e`` = the same metric through the public API with HOST
-(numpy, pinned) arrays -- H2D of u/h/s/C and D2H of the results inside the timed region;
-``roofline`` = the dominant kernel (FP64 DMMA quarter GEMM) timed live with CUDA events on its
-launching stream inside the timed region; ``cpu_baseline`` = the numpy oracle (the reference's own
-call sequence, oracle/qs_oracle.py) on the box's host cores.
+Every sharded leg builds its input in the ODQD form (each rank builds only its own planes), whose exact result is
+known in closed form (tests/closed_form.py); the leg asserts parity <= 1e-12 max|u'| inside the run, after the first
+``change_basis`` and after the last timed one (net transform), and prints it.
 
-``--impl reference`` times that CPU path alone (the reference is pure Python over numpy; the oracle
-issues the same numpy calls in the same order), all host threads, one bounded sample per step.
+Printed JSON line (rank 0).  ``value`` = whole-job TFLOP/s of the FOUR FULL quarter steps (symmetry test switched
+off: issued flops = the reference's 8 n^5 kappa), inputs resident in HBM, device-timed with CUDA events, max over
+ranks -- the same definition at every N.  The default API path detects exact (anti-)symmetry of ``u`` on the device
+and skips the mirror-image tiles; its time is reported beside it (``symmetry_path``).  ``e2e`` = the same metric
+through the public API from HOST arrays (H2D of the step's inputs and D2H of its results inside the timed region);
+``roofline`` = the dominant kernel (FP64 DMMA quarter GEMM) timed live with CUDA events on its launching stream;
+``cpu_baseline`` = the numpy oracle (the reference's own call sequence) on the box's host cores.
+
+``--impl reference`` times that CPU path alone, all host threads.
 """
 
 import argparse
@@ -31,12 +38,14 @@ import sys
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-if ROOT not in sys.path:
-    sys.path.insert(0, ROOT)
+for path in (ROOT, os.path.join(ROOT, "tests")):
+    if path not in sys.path:
+        sys.path.insert(0, path)
 
 METRIC = "change_basis FP64 TFLOP/s"
 UNIT = "TFLOP/s"
-N_BY_GPUS = {1: 128, 2: 148, 4: 168, 8: 192}
+N_BY_GPUS = {1: 128, 2: 148, 4: 168, 8: 192}  # weak series: n ~ 128 N^(1/5), even
+PARITY_TOL = 1e-12
 
 
 def parse_args():
@@ -45,25 +54,19 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=0, help="override the number of orbitals (development)")
+    ap.add_argument("--n", type=int, default=0, help="override the number of orbitals of the N = 1 workload (development)")
+    ap.add_argument("--legs", default="", help="comma list restricting the sharded legs (development): c5,c4,weak")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
 
-def transform_flops(n, m=None):
-    """Real flops of change_basis on (h, s, u): SURVEY.md section 8d."""
+def transform_flops(n, m=None, kappa=1):
+    """Real flops of change_basis on (h, s, u): SURVEY.md section 8d; kappa = 4 for complex (4M counting)."""
     m = n if m is None else m
     two_body = 2.0 * (n**4 * m + n**3 * m**2 + n**2 * m**3 + n * m**4)
     one_body = 2 * 2.0 * (n * n * m + n * m * m)  # h and s
-    return two_body + one_body
-
-
-def workload_n(args):
-    if args.n:
-        return args.n
-    gpus = max(args.gpus, 1)
-    return N_BY_GPUS.get(gpus, int(round(128 * gpus**0.2 / gpus)) * gpus)
+    return kappa * (two_body + one_body)
 
 
 def make_inputs(n, seed=2, with_u=True):
@@ -84,27 +87,56 @@ def make_inputs(n, seed=2, with_u=True):
     return out
 
 
-def make_u_planes(n, p0, p1, seed=2):
-    """Planes [p0, p1) of a sharded synthetic u: every plane has its own seeded stream, so any rank can
-    generate exactly its slab (no rank ever holds the whole tensor)."""
+def coefficients(n, complex_, seed=5):
+    """Basis-change coefficients of a sharded leg: real orthonormal ``C`` (``C_tilde = C^T``), or a well-conditioned
+    complex ``C = Q1 diag(0.5 .. 2) Q2`` with the bi-orthogonal ``C_tilde = C^-1``."""
     import numpy as np
 
-    out = np.empty((p1 - p0, n, n, n))
-    for p in range(p0, p1):
-        out[p - p0] = np.random.default_rng([seed, p]).standard_normal((n, n, n))
-    return out
+    rng = np.random.default_rng(seed)
+    if not complex_:
+        return np.ascontiguousarray(np.linalg.qr(rng.standard_normal((n, n)))[0]), None
+    q1 = np.linalg.qr(rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)))[0]
+    q2 = np.linalg.qr(rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)))[0]
+    C = q1 @ np.diag(rng.uniform(0.5, 2.0, n)) @ q2
+    return np.ascontiguousarray(C), np.ascontiguousarray(np.linalg.inv(C))
 
 
-def host_threads():
+def leg_specs(world):
+    """The sharded legs of an N-GPU run, headline first."""
+    c5 = {"key": "c5", "l": 200, "complex": False,
+          "workload": "configs[4]: GeneralOrbitalSystem from l=200 spatial (400 spin-orbitals, 204.8 GB real FP64 u): sharded "
+                      "ODQD grid build -> add_spin + anti_symmetrize_u -> change_basis, real orthonormal C"}
+    c4 = {"key": "c4", "l": 128, "complex": True,
+          "workload": "configs[3]: complex128 bi-orthogonal change_basis(C, C_tilde=C^-1), 256 spin-orbitals (68.7 GB u), "
+                      "anti-symmetrised GOS tensor from l=128 ODQD orbitals"}
+    n_weak = N_BY_GPUS.get(world, int(round(128 * world**0.2 / 2)) * 2)
+    weak = {"key": "weak", "l": n_weak // 2, "complex": False,
+            "workload": f"weak series: anti-symmetrised real GOS tensor, n={n_weak} spin-orbitals (n ~ 128 N^(1/5), equal "
+                        "flops per GPU), real orthonormal C"}
+    return [c5, c4, weak] if world >= 8 else [c4, weak]
+
+
+def use_all_host_cores():
+    """The CPU arm uses every host core whatever OMP_NUM_THREADS the launcher exported (torchrun sets it to 1).
+    OpenBLAS sizes its thread pool when numpy is first imported and cannot grow it later, so this must run before
+    that import."""
+    assert "numpy" not in sys.modules, "use_all_host_cores() must run before numpy is imported"
+    cores = str(os.cpu_count() or 1)
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = cores
+
+
+def blas_threads_all_cores():
+    """(threadpool limiter to keep alive, BLAS threads actually in effect for numpy)."""
+    cores = os.cpu_count() or 1
     try:
-        from threadpoolctl import threadpool_info
+        from threadpoolctl import threadpool_info, threadpool_limits
 
+        limiter = threadpool_limits(limits=cores)
         blas = [p["num_threads"] for p in threadpool_info() if p.get("user_api") == "blas"]
-        if blas:
-            return max(blas)
+        return limiter, (max(blas) if blas else cores)
     except Exception:
-        pass
-    return os.cpu_count() or 1
+        return None, cores
 
 
 # ------------------------------------------------------------------------------------------------
@@ -119,27 +151,70 @@ def cpu_change_basis_seconds(inputs):
     return dt, out
 
 
+def cpu_gos_pipeline(l, complex_, seed=5):
+    """The reference's call sequence of a sharded leg at a CPU-sized l: spatial u -> add_spin_two_body ->
+    anti_symmetrize_u (-> cast when complex) -> change_basis.  Returns (seconds of change_basis, seconds of
+    add_spin + anti-symmetrise)."""
+    import numpy as np
+
+    from oracle import qs_oracle as oracle
+
+    rng = np.random.default_rng(seed)
+    u = rng.standard_normal((l,) * 4)
+    h = rng.standard_normal((l, l))
+    t0 = time.perf_counter()
+    spin = oracle.anti_symmetrize_u(oracle.add_spin_two_body(u))
+    if complex_:
+        spin = spin.astype(np.complex128)
+    t_spin = time.perf_counter() - t0
+    h2 = oracle.add_spin_one_body(h).astype(spin.dtype)
+    C, Ct = coefficients(2 * l, complex_)
+    t0 = time.perf_counter()
+    oracle.change_basis({"h": h2, "s": np.eye(2 * l, dtype=spin.dtype), "u": spin}, C, Ct)
+    return time.perf_counter() - t0, t_spin
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # rank 0 alone runs the CPU arm
+    limiter, threads = blas_threads_all_cores()
     total = args.steps + args.warmup
-    n_full = workload_n(args)
-    # bound the run to a few minutes: probe at n = 64, extrapolate ~ n^5, shrink the sample if needed
-    probe, _ = cpu_change_basis_seconds(make_inputs(64, seed=3))
-    n = n_full
-    while n > 64 and probe * (n / 64.0) ** 5 * total > 150.0:
-        n -= 16
-    inputs = make_inputs(n)
-    for _ in range(args.warmup):
-        cpu_change_basis_seconds(inputs)
-    times = [cpu_change_basis_seconds(inputs)[0] for _ in range(args.steps)]
+    gpus = max(args.gpus, 1)
+    if gpus == 1:
+        n_full = args.n or N_BY_GPUS[1]
+        workload = workload_name_single(n_full)
+        # the full workload when `total` steps of it end within minutes, else the largest n that does
+        probe, _ = cpu_change_basis_seconds(make_inputs(64, seed=3))
+        n = n_full
+        while n > 64 and probe * (n / 64.0) ** 5 * total > 240.0:
+            n -= 16
+        inputs = make_inputs(n)
+        for _ in range(args.warmup):
+            cpu_change_basis_seconds(inputs)
+        times = [cpu_change_basis_seconds(inputs)[0] for _ in range(args.steps)]
+        kappa = 1
+        what = "oracle.change_basis = reference numpy call sequence (h, s, u)"
+    else:
+        spec = leg_specs(gpus)[0]
+        n_full, kappa = 2 * spec["l"], (4 if spec["complex"] else 1)
+        workload = spec["workload"]
+        # bounded sample: the same call sequence at a CPU-sized n (the full tensor needs 4 x 69-205 GB of host RAM)
+        probe, _ = cpu_gos_pipeline(24, spec["complex"])
+        n = 128
+        while n > 48 and probe * (n / 48.0) ** 5 * total > 240.0:
+            n -= 16
+        for _ in range(args.warmup):
+            cpu_gos_pipeline(n // 2, spec["complex"])
+        times = [cpu_gos_pipeline(n // 2, spec["complex"])[0] for _ in range(args.steps)]
+        what = "oracle add_spin_two_body + anti_symmetrize_u (untimed) -> oracle.change_basis (timed)"
     sec = sum(times) / len(times)
-    value = transform_flops(n) / sec * 1e-12
-    sample = (
-        f"full workload n={n}" if n == n_full else f"n={n} sample of the n={n_full} workload (throughput metric, "
-        f"bounded so {total} steps end within minutes)"
-    ) + "; oracle.change_basis = reference numpy call sequence (h, s, u)"
+    value = transform_flops(n, kappa=kappa) / sec * 1e-12
+    if n == n_full:
+        sample = f"full workload n={n}; {what}"
+    else:
+        sample = (f"n={n} sample of the n={n_full} workload; {what}; the throughput is taken as the estimate for the full "
+                  f"size (time extrapolated ~ n^5: {sec * (n_full / n) ** 5:.0f} s per change_basis at n={n_full})")
     line = {
         "impl": "reference",
         "metric": METRIC,
@@ -154,21 +229,18 @@ def run_reference_arm(args):
         "vs_baseline": None,
         "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": workload_name(args.gpus, n_full), "n": n_full, "n_timed": n},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": host_threads(), "kind": "port", "sample": sample},
+        "config": {"workload": workload, "n": n_full, "n_timed": n, "same_config": n == n_full},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "host_cores": os.cpu_count(), "kind": "port",
+                         "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+    del limiter
 
 
-def workload_name(gpus, n):
-    if gpus == 1:
-        return f"configs[1]: synthetic real FP64 BasisSet l={n}, random orthonormal C, change_basis on 1xB200"
-    return (
-        f"configs[1] scaled to {gpus} GPUs: real FP64 BasisSet l={n} (n ~ 128*N^(1/5), equal flops per GPU), u sharded "
-        "on its leading index, one all-to-all per change_basis"
-    )
+def workload_name_single(n):
+    return f"configs[1]: synthetic real FP64 BasisSet l={n}, random orthonormal C, change_basis on 1xB200"
 
 
 # ------------------------------------------------------------------------------------------------
@@ -230,277 +302,24 @@ class ClockSampler:
         }
 
 
-# ------------------------------------------------------------------------------------------------
-# the B200 arm
-# ------------------------------------------------------------------------------------------------
-def run_ours(args):
-    import numpy as np
-    import torch
-    import torch.distributed as dist
+class KernelTimer:
+    """The library's own event pairs around every quarter-GEMM launch (family 0) inside a timed region."""
 
-    from quantum_systems_b200 import BasisSet, _native, ops, xp
+    def __init__(self, lib, native):
+        self.lib, self.native = lib, native
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a CUDA device: quantum_systems_b200 has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    lib = _native.load()
-    n = workload_n(args)
-    flops = transform_flops(n)
+    def start(self):
+        self.lib.qs_kernel_timing_enable(1)
+        self.launches0 = self.lib.qs_launch_count()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def stop(self):
+        import ctypes
 
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    inputs = make_inputs(n, with_u=(world == 1))
-    peak_tflops = ops.probe_dmma_tflops()
-
-    # ---- leg 1: inputs resident in HBM -----------------------------------------------------------
-    if world == 1:
-        basis = BasisSet(n, 1, np=xp)
-        basis.h, basis.s, basis.u = inputs["h"], inputs["s"], inputs["u"]
-        C_dev = xp.asarray(inputs["C"])
-
-        def step():
-            basis.change_basis(C_dev)
-    else:
-        from quantum_systems_b200 import sharded
-
-        ctx = sharded.ProcessContext()
-        basis = sharded.ShardedBasisSet.from_slabs(
-            ctx, n, inputs["h"], inputs["s"], lambda p0, p1: make_u_planes(n, p0, p1)
-        )
-        C_dev = xp.asarray(inputs["C"])
-
-        def step():
-            basis.change_basis(C_dev)
-
-    for _ in range(args.warmup):
-        step()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    barrier()
-    lib.qs_kernel_timing_enable(1)
-    launches0 = lib.qs_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    barrier()
-    launches = lib.qs_launch_count() - launches0
-    ms = max_over_ranks(e0.elapsed_time(e1))
-    # dominant kernel: the quarter GEMM, timed by events around its own launches inside the region
-    import ctypes
-
-    k_ms, k_work, k_spans = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
-    _native.call("qs_kernel_timing_read", 0, ctypes.byref(k_ms), ctypes.byref(k_work), ctypes.byref(k_spans))
-    lib.qs_kernel_timing_enable(0)
-    ms_per_step = ms / args.steps
-    value = flops / (ms_per_step * 1e-3) * 1e-12
-    # `value` counts the ALGORITHMIC flops of the reference's four full quarter steps.  The
-    # synthetic u of configs[1] has the particle-exchange symmetry u_pqrs = u_qpsr (like every physical interaction
-    # and the reference's RandomBasisSet); the single-GPU path detects it exactly on the device and issues only the
-    # tiles that hold pairs r <= s in steps 2-4, so `value` can exceed the FP64 pipe peak while the roofline
-    # fraction below is computed from the flops actually ISSUED.
-    issued_flops_per_step = k_work.value / args.steps
-    if world == 1:
-        flags = ops.two_body_symmetry(basis.u)
-        symmetry_note = (
-            "u_pqrs = u_qpsr detected exactly per call and exploited: quarter steps 2-4 run on the tiles holding r <= s, "
-            "mirror fill" if flags & 2 else "none found in the input"
-        )
-    else:
-        symmetry_note = (
-            "none: the synthetic planes of the sharded workload are independent random numbers (the sharded schedule "
-            "exploits exact anti-symmetry u_pqrs = -u_pqsr when it finds it, e.g. BASELINE configs[3] and [4])"
-        )
-
-    # ---- leg 1b (one GPU): the same steps with the symmetry test switched off, i.e. the reference's four full
-    # quarter steps -- the number that is comparable with the sharded runs, whose synthetic planes carry no symmetry
-    value_full_steps = None
-    if world == 1:
-        ops.EXPLOIT_SYMMETRY = False
-        try:
-            for _ in range(max(args.warmup, 3)):
-                step()
-            torch.cuda.synchronize()
-            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            f0.record()
-            for _ in range(args.steps):
-                step()
-            f1.record()
-            torch.cuda.synchronize()
-            value_full_steps = flops / (f0.elapsed_time(f1) / args.steps * 1e-3) * 1e-12
-        finally:
-            ops.EXPLOIT_SYMMETRY = True
-
-    # ---- leg 2: end to end through the public API with host arrays -------------------------------
-    e2e = None
-    if not args.no_e2e and world == 1:
-        def pinned(a):
-            t = torch.empty(a.shape, dtype=torch.float64, pin_memory=True)
-            t.numpy()[...] = a
-            return t.numpy()
-
-        host_basis = BasisSet(n, 1, np=np)
-        host_basis.h, host_basis.s, host_basis.u = pinned(inputs["h"]), pinned(inputs["s"]), pinned(inputs["u"])
-        C_host = pinned(inputs["C"])
-        h2d = sum(a.nbytes for a in (host_basis.h, host_basis.s, host_basis.u, C_host))
-        e2e_steps = min(args.steps, 10)
-        for _ in range(max(args.warmup, 3)):
-            host_basis.change_basis(C_host)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            host_basis.change_basis(C_host)
-            assert isinstance(host_basis.u, np.ndarray)  # the result is back on the host
-        torch.cuda.synchronize()
-        e2e_s = (time.perf_counter() - t0) / e2e_steps
-        d2h = sum(a.nbytes for a in (host_basis.h, host_basis.s, host_basis.u))
-        e2e = {
-            "value": flops / e2e_s * 1e-12, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-            "api": "BasisSet(np=numpy).change_basis(C) on pinned host ndarrays",
-        }
-        del host_basis
-    elif world > 1 and not args.no_e2e:
-        # every rank keeps its slab of u in pinned host memory: H2D of the slab, sharded change_basis (peer
-        # stores over NVLink), D2H of the slab of the result
-        p0, p1 = basis.u.planes(rank)
-        host_in = torch.empty((p1 - p0, n, n, n), dtype=torch.float64, pin_memory=True)
-        host_in.copy_(basis.u.local())
-        host_out = torch.empty_like(host_in, pin_memory=True)
-        h_host = torch.empty((n, n), dtype=torch.float64, pin_memory=True).copy_(basis.h)
-        e2e_steps = min(args.steps, 10)
-
-        def e2e_step():
-            basis.u.local().copy_(host_in, non_blocking=True)
-            basis.h.copy_(h_host, non_blocking=True)
-            basis.change_basis(C_dev)
-            host_out.copy_(basis.u.local(), non_blocking=True)
-            h_host.copy_(basis.h, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-
-        for _ in range(3):
-            e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step()
-        barrier()
-        e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
-        slab_bytes = max_over_ranks(float(host_in.numel() * 8))
-        e2e = {
-            "value": flops / e2e_s * 1e-12, "unit": UNIT, "h2d_bytes_per_step": int(slab_bytes) + n * n * 8,
-            "d2h_bytes_per_step": int(slab_bytes) + n * n * 8, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-            "api": "per rank: pinned host slab -> ShardedBasisSet.change_basis(C) -> pinned host slab",
-        }
-    clocks = sampler.stop() if rank == 0 else None
-
-    if world > 1:
-        ctx.close()
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    # ---- roofline of the dominant kernel ---------------------------------------------------------
-    achieved = k_work.value / (k_ms.value * 1e-3) * 1e-12 if k_ms.value > 0 else None
-    traffic = None
-    prof = os.path.join(ROOT, "profiles", "quarter_gemm_traffic.json")
-    if os.path.exists(prof):
-        with open(prof) as fh:
-            traffic = json.load(fh).get(f"n{n}", {}).get("dram_bytes_per_launch")
-    # share of the four full quarter steps that was actually issued (1.0 without symmetry; the tiny one-body
-    # launches of h and s are timed too but carry ~1e-4 of the flops)
-    full_step_flops = 2.0 * n**5 / max(world, 1)
-    issued_share = (k_work.value / args.steps) / (4.0 * full_step_flops) if k_work.value else 1.0
-    step_bytes = 4.0 * 2.0 * 8 * n**4 / max(world, 1) * issued_share  # read A once, write the result once, per step
-    roofline = {
-        "kernel": "quarter_gemm_kernel (FP64 DMMA.8x8x4 + TMA)",
-        "bound": "tensor",
-        "achieved": achieved,
-        "peak": peak_tflops,
-        "unit": "TFLOP/s",
-        "frac": achieved / peak_tflops if achieved else None,
-        "traffic": traffic,
-        "peak_source": "FP64 tensor pipe measured in this run by a register-resident DMMA.8x8x4 loop "
-        "(qs_probe_dmma_tflops); MEASURED_PEAKS.json holds only bf16 and HBM-copy figures",
-        "launches_timed": int(k_spans.value),
-        "kernel_share_of_step": k_ms.value / ms if ms > 0 else None,
-        # per quarter step of u (four per change_basis); the one-body launches of h and s are negligible
-        "algorithmic_flops_per_launch": k_work.value / (4.0 * args.steps),
-        # one full quarter step reads 8 n^4 and writes 8 n^4 bytes; a masked step touches the issued share of it
-        "algorithmic_bytes_per_launch": step_bytes / 4.0,
-        "hbm_gbs_at_achieved": step_bytes * args.steps / (k_ms.value * 1e-3) * 1e-9 if k_ms.value > 0 else None,
-        "issued_share_of_full_steps": issued_share,
-        "hbm_peak_gbs_measured": _measured_peaks().get("hbm_gbs"),
-    }
-
-    # ---- CPU baseline (numpy oracle on this box's host cores) ------------------------------------
-    cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline:
-        sec, ref_out = cpu_change_basis_seconds(inputs)
-        cpu_baseline = {
-            "value": transform_flops(n) / sec * 1e-12, "unit": UNIT, "cores": host_threads(), "kind": "port",
-            "seconds": sec,
-            "sample": f"full workload once: oracle.change_basis (reference numpy call sequence) on the same n={n} inputs",
-        }
-        # the timed GPU path and the CPU path agree on this very input (north-star tolerance)
-        check = BasisSet(n, 1, np=xp)
-        check.h, check.s, check.u = inputs["h"], inputs["s"], inputs["u"]
-        check.change_basis(C_dev)
-        err = float(np.abs(check.u.cpu().numpy() - ref_out["u"]).max()) / float(np.abs(ref_out["u"]).max())
-        cpu_baseline["max_rel_err_vs_gpu"] = err
-        assert err <= 1e-12, f"GPU change_basis deviates from the CPU oracle: {err:.3e}"
-
-    line = {
-        "metric": METRIC,
-        "value": value,
-        "unit": UNIT,
-        "n_gpus": world,
-        "steps": args.steps,
-        "warmup": args.warmup,
-        "ms_per_step": ms_per_step,
-        "wall_s_per_change_basis": ms_per_step * 1e-3,
-        "higher_is_better": True,
-        "scaling": "weak",
-        "vs_baseline": None,
-        "dtype": "f64",
-        "data": "synthetic",
-        "config": {
-            "workload": workload_name(world, n),
-            "n": n,
-            "flops_per_step": flops,
-            "l2": "inputs (8*n^4 bytes per tensor pass) exceed the 126 MB L2; no explicit flush",
-            "symmetry": symmetry_note,
-            "issued_flops_per_step": issued_flops_per_step,
-            "value_four_full_steps": value_full_steps,
-        },
-        "e2e": e2e,
-        "gpu_launches": int(launches),
-        "roofline": roofline,
-        "cpu_baseline": cpu_baseline,
-        "clocks": clocks,
-    }
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+        ms, work, spans = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
+        self.native.call("qs_kernel_timing_read", 0, ctypes.byref(ms), ctypes.byref(work), ctypes.byref(spans))
+        launches = self.lib.qs_launch_count() - self.launches0
+        self.lib.qs_kernel_timing_enable(0)
+        return {"ms": ms.value, "flops": work.value, "spans": int(spans.value), "launches": int(launches)}
 
 
 def _measured_peaks():
@@ -511,8 +330,554 @@ def _measured_peaks():
         return {}
 
 
+def roofline_entry(kernel, ms_region, peak_tflops, n_launch_flops, n_launch_bytes, traffic):
+    achieved = kernel["flops"] / (kernel["ms"] * 1e-3) * 1e-12 if kernel["ms"] > 0 else None
+    return {
+        "kernel": "quarter_gemm_kernel (FP64 DMMA.8x8x4 + TMA)",
+        "bound": "tensor",
+        "achieved": achieved,
+        "peak": peak_tflops,
+        "unit": "TFLOP/s",
+        "frac": achieved / peak_tflops if achieved else None,
+        "traffic": traffic,
+        "peak_source": "FP64 tensor pipe measured in this run by a register-resident DMMA.8x8x4 loop "
+        "(qs_probe_dmma_tflops); MEASURED_PEAKS.json holds only bf16 and HBM-copy figures",
+        "launches_timed": kernel["spans"],
+        "kernel_share_of_step": kernel["ms"] / ms_region if ms_region > 0 else None,
+        "algorithmic_flops_per_launch": n_launch_flops,
+        "algorithmic_bytes_per_launch": n_launch_bytes,
+        "hbm_peak_gbs_measured": _measured_peaks().get("hbm_gbs"),
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# one GPU: configs[1]
+# ------------------------------------------------------------------------------------------------
+def run_single(args, torch, lib):
+    import numpy as np
+
+    from quantum_systems_b200 import ODQD, BasisSet, GeneralOrbitalSystem, _native, ops, xp
+
+    n = args.n or N_BY_GPUS[1]
+    flops = transform_flops(n)
+    inputs = make_inputs(n)
+    peak_tflops = ops.probe_dmma_tflops()
+    timer = KernelTimer(lib, _native)
+
+    C_dev = xp.asarray(inputs["C"])
+
+    def fresh_basis():
+        # every timed phase starts from the exactly symmetric input: after a full-step transform the symmetry holds
+        # to rounding only, and the device-side test (exact by design) would rightly not find it
+        basis = BasisSet(n, 1, np=xp)
+        basis.h, basis.s, basis.u = inputs["h"], inputs["s"], inputs["u"]
+        return basis
+
+    def timed_steps(step, steps, warmup):
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        timer.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), timer.stop()
+
+    sampler = ClockSampler(torch.cuda.current_device())
+    sampler.start()
+    # ---- leg 1 (headline): the reference's four full quarter steps, inputs resident in HBM ------------------
+    basis = fresh_basis()
+    ops.EXPLOIT_SYMMETRY = False
+    try:
+        ms, kernel = timed_steps(lambda: basis.change_basis(C_dev), args.steps, args.warmup)
+    finally:
+        ops.EXPLOIT_SYMMETRY = True
+    ms_per_step = ms / args.steps
+    value = flops / (ms_per_step * 1e-3) * 1e-12
+
+    # ---- leg 1b: the default API path (exact symmetry of u detected on the device, mirror tiles skipped) ----
+    basis = fresh_basis()
+    flags = ops.two_body_symmetry(basis.u)
+    ms_sym, kernel_sym = timed_steps(lambda: basis.change_basis(C_dev), args.steps, max(args.warmup, 3))
+    flags_after = ops.two_body_symmetry(basis.u)
+    symmetry_path = {
+        "found": "u_pqrs = u_qpsr (particle exchange)" if flags & 2 else ("u_pqrs = -u_pqsr" if flags & 1 else "none"),
+        "still_exact_after_timed_steps": bool(flags_after & flags),
+        "ms_per_step": ms_sym / args.steps,
+        "effective_tflops": flops / (ms_sym / args.steps * 1e-3) * 1e-12,
+        "issued_share_of_full_steps": kernel_sym["flops"] / kernel["flops"] if kernel["flops"] else None,
+        "kernel_share_of_step": kernel_sym["ms"] / ms_sym if ms_sym else None,
+        "note": "default path of change_basis: quarter steps 2-4 run on the tiles holding r <= s, then a mirror fill; "
+                "effective = the reference's 8 n^5 flops / time, so it may exceed the FP64 pipe peak",
+    }
+    del basis
+
+    # ---- weak-series leg at N = 1: anti-symmetrised real GOS tensor, n = 128 ---------------------------------
+    weak = None
+    if not args.n:
+        def fresh_gos():
+            od = ODQD(n // 2, 20.0, 2 * n + 1, np=xp)
+            od.cast_to_complex_on_spin_doubling = False
+            return GeneralOrbitalSystem(2, od)
+
+        Cw = xp.asarray(coefficients(n, False)[0])
+        gos = fresh_gos()
+        ops.EXPLOIT_SYMMETRY = False
+        try:
+            ms_w, _ = timed_steps(lambda: gos.change_basis(Cw), args.steps, args.warmup)
+        finally:
+            ops.EXPLOIT_SYMMETRY = True
+        gos = fresh_gos()
+        ms_ws, kernel_ws = timed_steps(lambda: gos.change_basis(Cw), args.steps, args.warmup)
+        weak = {
+            "workload": leg_specs(1)[-1]["workload"].replace("n=128", f"n={n}"), "n": n,
+            "ms_per_step": ms_w / args.steps, "value": transform_flops(n) / (ms_w / args.steps * 1e-3) * 1e-12,
+            "symmetry_path": {"ms_per_step": ms_ws / args.steps,
+                              "effective_tflops": transform_flops(n) / (ms_ws / args.steps * 1e-3) * 1e-12,
+                              "issued_flops_per_step": kernel_ws["flops"] / args.steps,
+                              "still_exact_after_timed_steps": bool(ops.two_body_symmetry(gos.u) & 1)},
+        }
+        del gos, Cw
+
+    # ---- leg 2: end to end through the public API with host arrays -------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        def pinned(a):
+            t = torch.empty(a.shape, dtype=torch.float64, pin_memory=True)
+            t.numpy()[...] = a
+            return t.numpy()
+
+        def e2e_loop(arrays, steps):
+            host_basis = BasisSet(n, 1, np=np)
+            host_basis.h, host_basis.s, host_basis.u = arrays["h"], arrays["s"], arrays["u"]
+            for _ in range(3):
+                host_basis.change_basis(arrays["C"])
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                host_basis.change_basis(arrays["C"])
+                assert isinstance(host_basis.u, np.ndarray)  # the result is back on the host
+            torch.cuda.synchronize()
+            seconds = (time.perf_counter() - t0) / steps
+            d2h = sum(a.nbytes for a in (host_basis.h, host_basis.s, host_basis.u))
+            return seconds, d2h
+
+        e2e_steps = min(args.steps, 10)
+        pinned_in = {k: pinned(v) for k, v in inputs.items()}
+        h2d = sum(a.nbytes for a in pinned_in.values())
+        e2e_s, d2h = e2e_loop(pinned_in, e2e_steps)
+        # the reference's user hands over ordinary (pageable) ndarrays
+        pageable_s, _ = e2e_loop({k: np.array(v) for k, v in inputs.items()}, e2e_steps)
+        e2e = {
+            "value": flops / e2e_s * 1e-12, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+            "api": "BasisSet(np=numpy).change_basis(C) on pinned host ndarrays",
+            "pageable_inputs": {"value": flops / pageable_s * 1e-12, "ms_per_step": pageable_s * 1e3,
+                                "note": "same call on ordinary numpy arrays (not pinned by the caller)"},
+        }
+    clocks = sampler.stop()
+
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "quarter_gemm_traffic.json")
+    if os.path.exists(prof):
+        with open(prof) as fh:
+            traffic = json.load(fh).get(f"n{n}", {}).get("dram_bytes_per_launch")
+    roofline = roofline_entry(kernel, ms, peak_tflops, 2.0 * n**5, 2.0 * 8 * n**4, traffic)
+    roofline["traffic_source"] = "ncu --set full capture of one full-step launch (profiles/quarter_gemm_traffic.json)"
+
+    # ---- CPU baseline (numpy oracle on this box's host cores) and parity of the timed path -------------------
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        limiter, threads = blas_threads_all_cores()
+        sec, ref_out = cpu_change_basis_seconds(inputs)
+        cpu_baseline = {
+            "value": transform_flops(n) / sec * 1e-12, "unit": UNIT, "cores": threads, "kind": "port", "seconds": sec,
+            "sample": f"full workload once: oracle.change_basis (reference numpy call sequence) on the same n={n} inputs",
+        }
+        del limiter
+        scale = float(np.abs(ref_out["u"]).max())
+        for name, exploit in (("max_rel_err_vs_gpu_full_steps", False), ("max_rel_err_vs_gpu", True)):
+            check = BasisSet(n, 1, np=xp)
+            check.h, check.s, check.u = inputs["h"], inputs["s"], inputs["u"]
+            ops.EXPLOIT_SYMMETRY = exploit
+            try:
+                check.change_basis(C_dev)
+            finally:
+                ops.EXPLOIT_SYMMETRY = True
+            cpu_baseline[name] = float(np.abs(check.u.cpu().numpy() - ref_out["u"]).max()) / scale
+            assert cpu_baseline[name] <= PARITY_TOL, f"GPU change_basis deviates from the CPU oracle: {cpu_baseline[name]:.3e}"
+            del check
+
+    return {
+        "metric": METRIC,
+        "value": value,
+        "unit": UNIT,
+        "n_gpus": 1,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": ms_per_step,
+        "wall_s_per_change_basis": ms_per_step * 1e-3,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f64",
+        "data": "synthetic",
+        "config": {
+            "workload": workload_name_single(n),
+            "n": n,
+            "flops_per_step": flops,
+            "value_definition": "four full quarter steps (symmetry test off): issued flops = the reference's 8 n^5",
+            "l2": "inputs (8*n^4 bytes per tensor pass) exceed the 126 MB L2; no explicit flush",
+            "symmetry_path": symmetry_path,
+            "legs": {"weak": weak},
+        },
+        "e2e": e2e,
+        "gpu_launches": kernel["launches"],
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "clocks": clocks,
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# N GPUs: one tensor sharded over the ranks
+# ------------------------------------------------------------------------------------------------
+def run_sharded_leg(spec, args, ctx, torch, dist, lib, peak_tflops, with_e2e):
+    """Sharded ODQD grid build -> add_spin + anti-symmetrise -> change_basis on `world` GPUs; returns the leg's
+    dictionary (rank-independent numbers are max / sum over ranks)."""
+    import numpy as np
+
+    import closed_form
+    from quantum_systems_b200 import _native, sharded
+    from quantum_systems_b200.odqd import grid_orbitals
+    from quantum_systems_b200.potentials import HOPotential
+
+    rank, world = ctx.rank, ctx.world
+    l = spec["l"]
+    n = 2 * l
+    complex_ = spec["complex"]
+    dtype = torch.complex128 if complex_ else torch.float64
+    kappa = 4 if complex_ else 1
+    flops = transform_flops(n, kappa=kappa)
+    n_occ = min(20, n // 4)
+    timer = KernelTimer(lib, _native)
+
+    def reduce(x, op):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def device_timed(fn):
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        return reduce(e0.elapsed_time(e1), dist.ReduceOp.MAX)
+
+    # ---- input: every rank builds only the spatial planes behind its own spin-orbital planes ----------------
+    grid, eps, Lg = grid_orbitals(l, 20.0, 4 * l + 1, HOPotential(0.25))
+    inner = grid[1:-1]
+    W = closed_form.shielded_coulomb(inner, 1.0, 0.25)
+    C, Ct = coefficients(n, complex_)
+    C_dev = torch.from_numpy(C).cuda()
+    Ct_dev = torch.from_numpy(Ct).cuda() if Ct is not None else None
+    pairs = [(C_dev, Ct_dev)] if Ct is None else [(C_dev, Ct_dev), (Ct_dev, C_dev)]  # bi-orthogonal: C, then its inverse
+
+    target = sharded.ShardedTwoBody.empty(ctx, n, dtype)  # peer-visible buffers (u and the ping-pong spare)
+    p0, p1 = target.planes(rank)
+    sp0, sp1 = (p0 // 2, (p1 - 1) // 2 + 1) if p1 > p0 else (0, 0)
+    builder = sharded.odqd_spatial_planes(Lg, inner, 1.0, 0.25)
+    slab = {}
+    ms_build = device_timed(lambda: slab.update(u=builder(sp0, sp1)))
+    spatial = lambda a0, a1: slab["u"][a0 - sp0 : a1 - sp0]  # noqa: E731
+    h_spatial, s_spatial = np.diag(eps), np.eye(l)
+
+    state = {}
+    applied = []  # which (C, C_tilde) pair every change_basis since the last spin doubling used (net transform)
+
+    def spin_double(into=None):
+        """(Re)build the anti-symmetrised spin-orbital tensor from the spatial planes -- into `into`, or into the spare
+        buffers of the current tensor.  Every phase starts from it: after a full-step transform the anti-symmetry
+        holds to rounding only, and the device-side test (exact by design) would rightly not find it."""
+        if into is None:
+            into = state["basis"].u.successor()
+        state["basis"] = sharded.ShardedBasisSet.from_spatial_planes(ctx, h_spatial, s_spatial, l, spatial,
+                                                                     out_dtype=dtype, into=into)
+        applied.clear()
+
+    spin_double(target)  # warm-up of the fused pass
+    ms_spin = min(device_timed(lambda: spin_double(target)) for _ in range(3))
+    spin_bytes = 8.0 * l**4 + (16 if complex_ else 8) * float(n) ** 4  # aggregate algorithmic bytes (SURVEY 8d)
+
+    def check(net_C, net_Ct, tensor):
+        form = closed_form.SpinDoubledClosedForm(Lg, W, net_C, net_Ct)
+        q0, q1 = tensor.planes(rank)
+        local = tensor.local() if q1 > q0 else torch.empty((0, n, n, n), dtype=dtype, device="cuda")
+        errs = closed_form.check_shard(closed_form.TorchSlab(local), q0, form, np.random.default_rng(rank))
+        scale = reduce(errs[3], dist.ReduceOp.MAX)
+        return [reduce(e, dist.ReduceOp.MAX) / scale for e in errs[:3]], form
+
+    def step():
+        Cd, Ctd = pairs[len(applied) % len(pairs)]
+        state["basis"].change_basis(Cd, Ctd)
+        applied.append(len(applied) % len(pairs))
+
+    def net_transform():
+        net_C = np.eye(n, dtype=C.dtype)
+        net_Ct = np.eye(n, dtype=C.dtype)
+        host_pairs = [(C, C.conj().T)] if Ct is None else [(C, Ct), (Ct, C)]
+        for which in applied:
+            Ck, Ctk = host_pairs[which]
+            net_C, net_Ct = net_C @ Ck, Ctk @ net_Ct
+        return net_C, net_Ct
+
+    def timed_loop(exploit):
+        sharded.EXPLOIT_SYMMETRY = exploit
+        try:
+            for _ in range(args.warmup):
+                step()
+            torch.cuda.synchronize()
+            dist.barrier()
+            timer.start()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            dist.barrier()
+            kernel = timer.stop()
+        finally:
+            sharded.EXPLOIT_SYMMETRY = True
+        return reduce(e0.elapsed_time(e1), dist.ReduceOp.MAX), kernel
+
+    # ---- timed: four full quarter steps (headline), parity of the first call and of the net transform ---------
+    sharded.EXPLOIT_SYMMETRY = False
+    step()
+    sharded.EXPLOIT_SYMMETRY = True
+    parity_full_first, _ = check(*net_transform(), state["basis"].u)
+    spin_double()
+    ms_full, kernel_full = timed_loop(False)
+    parity_full_last, _ = check(*net_transform(), state["basis"].u)
+    calls_full = len(applied)
+    # ---- timed: the default symmetry-aware path, same checks -------------------------------------------------
+    spin_double()
+    step()
+    parity_sym_first, _ = check(*net_transform(), state["basis"].u)
+    spin_double()
+    ms_sym, kernel_sym = timed_loop(True)
+    parity_last, form_last = check(*net_transform(), state["basis"].u)
+    still_antisymmetric = sharded.is_antisymmetric_last_pair(state["basis"].u)
+    basis = state["basis"]
+
+    # consumer on the sharded result: general Fock matrix (n^2 all-reduce) against the closed form, rank 0 checks
+    f = basis.construct_fock_matrix(basis.h, basis.u, n_occ).cpu().numpy()
+    fock_err = 0.0
+    if rank == 0:
+        ref_f = basis.h.cpu().numpy() + form_last.fock_two_body(n_occ)
+        fock_err = float(np.abs(f - ref_f).max() / np.abs(ref_f).max())
+    fock_err = reduce(fock_err, dist.ReduceOp.MAX)
+
+    issued_full = reduce(kernel_full["flops"], dist.ReduceOp.SUM)
+    issued_sym = reduce(kernel_sym["flops"], dist.ReduceOp.SUM)
+    kernel_ms_max = reduce(kernel_full["ms"], dist.ReduceOp.MAX)
+    frac_min = reduce(kernel_full["flops"] / (kernel_full["ms"] * 1e-3) * 1e-12 / peak_tflops if kernel_full["ms"] else 0.0,
+                      dist.ReduceOp.MIN)
+    ms_step = ms_full / args.steps
+    names = ("planes", "samples", "antisymmetry_defect")
+    leg = {
+        "workload": spec["workload"],
+        "n": n, "dtype": "c128" if complex_ else "f64", "tensor_gb": (16 if complex_ else 8) * float(n) ** 4 / 1e9,
+        "flops_per_step": flops,
+        "ms_per_step": ms_step,
+        "wall_s_per_change_basis": ms_step * 1e-3,
+        "value": flops / (ms_step * 1e-3) * 1e-12,
+        "issued_flops_per_step": issued_full / args.steps,
+        "fraction_of_aggregate_dmma_peak": flops / (ms_step * 1e-3) * 1e-12 / (peak_tflops * world),
+        "symmetry_path": {
+            "found": "u_pqrs = -u_pqsr, detected exactly on every rank's slab per call",
+            "ms_per_step": ms_sym / args.steps,
+            "effective_tflops": flops / (ms_sym / args.steps * 1e-3) * 1e-12,
+            "issued_share_of_full_steps": issued_sym / issued_full if issued_full else None,
+        },
+        "odqd_planes_build_ms": ms_build,
+        "add_spin_antisym_ms": ms_spin,
+        "add_spin_antisym_aggregate_gbs": spin_bytes / (ms_spin * 1e-3) * 1e-9,
+        "parity": {
+            "tolerance": PARITY_TOL,
+            "method": "closed form of the ODQD-structured input (tests/closed_form.py): whole planes + 2000 random "
+                      "elements of every rank's shard, max over ranks, relative to max|u'|",
+            "full_steps_first_change_basis": dict(zip(names, parity_full_first)),
+            "full_steps_after_last_timed_step_net_transform": dict(zip(names, parity_full_last)),
+            "symmetry_path_first_change_basis": dict(zip(names, parity_sym_first)),
+            "symmetry_path_after_last_timed_step_net_transform": dict(zip(names, parity_last)),
+            "symmetry_path_result_exactly_antisymmetric": bool(still_antisymmetric),
+            "fock_matrix_rel_err": fock_err,
+            "change_basis_calls_behind_net_transform": [calls_full, len(applied)],
+        },
+        "kernel": {"quarter_gemm_ms_max_rank": kernel_ms_max, "share_of_step": kernel_ms_max / ms_full if ms_full else None,
+                   "frac_of_dmma_peak_min_rank": frac_min, "launches_rank0": kernel_full["launches"],
+                   "rank0": kernel_full},
+    }
+    worst = max(parity_full_first[:2] + parity_full_last[:2] + parity_sym_first[:2] + parity_last[:2] + [fock_err])
+    leg["parity"]["ok"] = bool(worst <= PARITY_TOL and still_antisymmetric
+                               and max(parity_sym_first[2], parity_last[2]) == 0.0)
+
+    # ---- end to end: pinned host planes of the SPATIAL tensor -> H2D -> add_spin + anti-symmetrise -> change_basis
+    #      -> Fock matrix + reference energy -> D2H (the sharded result itself stays in HBM for its consumers) ----
+    if with_e2e and not args.no_e2e:
+        count = slab["u"].numel()
+        host_slab = torch.empty((max(sp1 - sp0, 0), l, l, l), dtype=torch.float64, pin_memory=True)
+        host_slab.copy_(slab["u"])
+        host_f = torch.empty((n, n), dtype=dtype, pin_memory=True)
+        e2e_steps = min(args.steps, 10)
+        out = {}
+
+        def e2e_step():
+            slab["u"].copy_(host_slab, non_blocking=True)
+            spin_double()
+            basis = state["basis"]
+            basis.change_basis(C_dev, Ct_dev)
+            host_f.copy_(basis.construct_fock_matrix(basis.h, basis.u, n_occ), non_blocking=True)
+            out["energy"] = basis.compute_reference_energy(n_occ)  # D2H of the reduced traces, synchronises
+
+        for _ in range(2):
+            e2e_step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e2e_s = reduce((time.perf_counter() - t0) / e2e_steps, dist.ReduceOp.MAX)
+        parity_e2e, _ = check(C, Ct, state["basis"].u)
+        leg["parity"]["after_e2e_steps"] = dict(zip(names, parity_e2e))
+        leg["parity"]["ok"] = bool(leg["parity"]["ok"] and max(parity_e2e[:2]) <= PARITY_TOL)
+        leg["e2e"] = {
+            "value": flops / e2e_s * 1e-12, "unit": UNIT,
+            "h2d_bytes_per_step": int(reduce(float(count * 8), dist.ReduceOp.SUM)),
+            "d2h_bytes_per_step": int(host_f.numel() * host_f.element_size() + 48),
+            "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+            "api": "per rank: pinned host planes of the spatial tensor -> ShardedBasisSet.from_spatial_planes (add_spin + "
+                   "anti_symmetrize_u) -> change_basis(C, C_tilde) -> construct_fock_matrix + compute_reference_energy -> host; "
+                   "the sharded 4-index result stays in HBM for its consumers",
+            "reference_energy": complex(out["energy"]).real,
+        }
+        del host_slab
+    state.clear()
+    slab.clear()
+    del basis, target
+    return leg
+
+
+def run_sharded(args, torch, dist, lib, rank, world, local_rank):
+    from quantum_systems_b200 import ops, sharded
+
+    peak_tflops = ops.probe_dmma_tflops()
+    specs = leg_specs(world)
+    if args.legs:
+        specs = [s for s in specs if s["key"] in args.legs.split(",")]
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    legs = {}
+    for i, spec in enumerate(specs):
+        ctx = sharded.ProcessContext()
+        try:
+            legs[spec["key"]] = run_sharded_leg(spec, args, ctx, torch, dist, lib, peak_tflops, with_e2e=True)
+        finally:
+            ctx.close()  # unmap and free the peer buffers before the next leg allocates its own
+            torch.cuda.empty_cache()
+    clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        return None
+    head_spec, head = specs[0], legs[specs[0]["key"]]
+    n = head["n"]
+    kappa = 4 if head_spec["complex"] else 1
+    # per rank and quarter step: 2 n^5 kappa / world flops; the tensor pass reads and writes n^4 / world elements
+    roofline = roofline_entry(head["kernel"]["rank0"], head["ms_per_step"] * args.steps, peak_tflops,
+                              2.0 * n**5 * kappa / world, 2.0 * (16 if head_spec["complex"] else 8) * float(n) ** 4 / world,
+                              None)
+    roofline["frac_min_over_ranks"] = head["kernel"]["frac_of_dmma_peak_min_rank"]
+    return {
+        "metric": METRIC,
+        "value": head["value"],
+        "unit": UNIT,
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": head["ms_per_step"],
+        "wall_s_per_change_basis": head["wall_s_per_change_basis"],
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f64",
+        "data": "synthetic",
+        "config": {
+            "workload": head["workload"],
+            "n": n,
+            "flops_per_step": head["flops_per_step"],
+            "value_definition": "four full quarter steps (symmetry test off): issued flops = the reference's 8 n^5 kappa "
+                                "(kappa = 4 for complex128, 4M counting); the default symmetry-aware path is in symmetry_path",
+            "l2": "every tensor pass exceeds the 126 MB L2; no explicit flush",
+            "parity_ok": all(leg["parity"]["ok"] for leg in legs.values()),
+            "fraction_of_aggregate_dmma_peak": head["fraction_of_aggregate_dmma_peak"],
+            "add_spin_antisym_ms": head["add_spin_antisym_ms"],
+            "add_spin_antisym_aggregate_gbs": head["add_spin_antisym_aggregate_gbs"],
+            "symmetry_path": head["symmetry_path"],
+            "parity": head["parity"],
+            "legs": legs,
+        },
+        "e2e": head.get("e2e"),
+        "gpu_launches": head["kernel"]["launches_rank0"],
+        "roofline": roofline,
+        "cpu_baseline": None,
+        "clocks": clocks,
+    }
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from quantum_systems_b200 import _native
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: quantum_systems_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    lib = _native.load()
+    if world == 1:
+        line = run_single(args, torch, lib)
+        print(json.dumps(line), flush=True)
+        return
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        line = run_sharded(args, torch, dist, lib, rank, world, local_rank)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+            if not line["config"]["parity_ok"]:
+                raise SystemExit("parity check failed: see config.legs[*].parity")
+    finally:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    if (args.impl == "reference" and rank == 0) or (args.impl == "ours" and world == 1):
+        use_all_host_cores()  # the CPU arm / cpu_baseline leg: all host threads
     if args.impl == "reference":
         run_reference_arm(args)
     else:

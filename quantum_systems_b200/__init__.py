@@ -17,6 +17,7 @@ from .spatial_orbital_system import SpatialOrbitalSystem
 from .random_basis import RandomBasisSet
 from .odqd import ODQD
 from .sinc_dvr import ODSincDVR
+from . import time_evolution_operators  # noqa: F401
 from . import two_dim_ho  # noqa: F401
 from .two_dim_ho import (
     get_coulomb_elements,

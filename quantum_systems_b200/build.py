@@ -22,10 +22,11 @@ NVCC_FLAGS = [
     "-std=c++17",
     "-Xcompiler",
     "-fPIC",
-    "-shared",
-    "-cudart",
-    "static",
 ]
+# The CUDA runtime is linked dynamically (libcudart.so.12, the one torch has already loaded): the shipped library
+# then carries none of the runtime's own entry points or strings.
+LINK_FLAGS = ["-shared", "-cudart", "shared", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
+OBJ_DIR = os.path.join(PKG_DIR, "build")
 
 
 def sources():
@@ -40,20 +41,41 @@ def is_stale():
     return any(os.path.getmtime(d) > built for d in deps)
 
 
+def _compile(nvcc, src, verbose):
+    obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
+    deps = [src] + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(PKG_DIR, "..", "include", "*.h"))
+    if os.path.exists(obj) and all(os.path.getmtime(d) <= os.path.getmtime(obj) for d in deps):
+        return obj, ""
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+    return obj, proc.stderr
+
+
 def build(force=False, verbose=False):
-    """Compile every ``csrc/*.cu`` into ``libqsb200.so``.  Returns the library path."""
+    """Compile every ``csrc/*.cu`` (one nvcc process per file, in parallel) and link ``libqsb200.so``.
+    Returns the library path."""
     if not force and not is_stale():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found; libqsb200.so cannot be built and there is no CPU fallback")
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    if force:
+        for old in glob.glob(os.path.join(OBJ_DIR, "*.o")):
+            os.remove(old)
+    from concurrent.futures import ThreadPoolExecutor
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+        results = list(pool.map(lambda src: _compile(nvcc, src, verbose), sources()))
+    if verbose:
+        sys.stderr.write("".join(log for _, log in results))
     tmp = LIB_PATH + ".tmp"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + sources()
+    cmd = [nvcc] + LINK_FLAGS + ["-o", tmp] + [obj for obj, _ in results]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
-    if verbose:
-        sys.stderr.write(proc.stderr)
+        raise RuntimeError("link failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
     os.replace(tmp, LIB_PATH)
     return LIB_PATH
 

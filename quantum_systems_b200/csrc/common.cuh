@@ -53,8 +53,21 @@ void qs_count_launch();
 bool qs_timing_begin(int family, double work, void* stream, int* slot);
 void qs_timing_end(int slot, void* stream);
 
-// Number of SMs of the current device (cached).
+// Number of SMs of the current device, and the device ordinal itself (clamped to [0, kMaxDevices)); both
+// caches are per device so that one process may drive several GPUs.
+constexpr int kMaxDevices = 64;
+int qs_current_device();
 int qs_sm_count();
+
+// Shape-dependent index tables (tile lists of masked launches, pair tables of the packed layouts) are the same for
+// every call with the same extents.  They are built on the host ONCE per (device, key), uploaded with a blocking
+// copy and kept in device memory for the life of the process, so that a steady-state transform issues no
+// host-to-device copy at all (a cudaMemcpyAsync from pageable memory synchronises the stream first and drains the
+// launch queue).  `key` is any byte string that determines the contents; returns nullptr when the cache is full
+// (the caller then stages the table through its workspace as before).
+const void* qs_table_cache_get(const void* key, size_t key_bytes);
+const void* qs_table_cache_put(const void* key, size_t key_bytes, const void* host_data, size_t bytes);
+uint64_t qs_hash_bytes(const void* data, size_t bytes, uint64_t seed);
 
 // Internal (not part of the C ABI): symmetry mask of a quarter transform (see quarter_gemm.cu, tile_wanted) and
 // the masked launch used by the symmetry-aware four-index transform (transform.cu).

@@ -2,6 +2,9 @@
 #include <stdarg.h>
 
 #include <atomic>
+#include <mutex>
+#include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "common.cuh"
@@ -17,15 +20,86 @@ void qs_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+// Device properties are cached PER DEVICE: a process may drive several GPUs (cudaSetDevice between calls).
+int qs_current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+    return dev;
+}
+
 int qs_sm_count() {
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
-            sms = 148;
+    static int sms[kMaxDevices] = {0};
+    const int dev = qs_current_device();
+    if (sms[dev] == 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        sms[dev] = v;
     }
-    return sms;
+    return sms[dev];
+}
+
+// ---------------------------------------------------------------------------------------------
+// device-resident cache of shape-dependent index tables (see common.cuh)
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct CachedTable {
+    std::string key;
+    void* dev;
+};
+std::mutex g_table_mutex;
+std::unordered_multimap<uint64_t, CachedTable>* g_tables = nullptr;
+size_t g_table_bytes = 0;
+constexpr size_t kTableCacheLimit = 512u << 20;  // bytes of device memory over all devices
+}  // namespace
+
+uint64_t qs_hash_bytes(const void* data, size_t bytes, uint64_t seed) {
+    const unsigned char* p = static_cast<const unsigned char*>(data);
+    uint64_t h = 1469598103934665603ull ^ seed;  // FNV-1a
+    for (size_t i = 0; i < bytes; ++i) {
+        h ^= p[i];
+        h *= 1099511628211ull;
+    }
+    return h;
+}
+
+static std::string full_key(const void* key, size_t key_bytes) {
+    const int dev = qs_current_device();
+    std::string k(reinterpret_cast<const char*>(&dev), sizeof(dev));
+    k.append(static_cast<const char*>(key), key_bytes);
+    return k;
+}
+
+const void* qs_table_cache_get(const void* key, size_t key_bytes) {
+    const std::string k = full_key(key, key_bytes);
+    const uint64_t h = qs_hash_bytes(k.data(), k.size(), 0);
+    std::lock_guard<std::mutex> lock(g_table_mutex);
+    if (!g_tables) return nullptr;
+    auto range = g_tables->equal_range(h);
+    for (auto it = range.first; it != range.second; ++it)
+        if (it->second.key == k) return it->second.dev;
+    return nullptr;
+}
+
+const void* qs_table_cache_put(const void* key, size_t key_bytes, const void* host_data, size_t bytes) {
+    const std::string k = full_key(key, key_bytes);
+    const uint64_t h = qs_hash_bytes(k.data(), k.size(), 0);
+    std::lock_guard<std::mutex> lock(g_table_mutex);
+    if (!g_tables) g_tables = new std::unordered_multimap<uint64_t, CachedTable>();
+    if (g_table_bytes + bytes > kTableCacheLimit) return nullptr;
+    void* dev = nullptr;
+    if (cudaMalloc(&dev, bytes ? bytes : 16) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    // blocking copy: the table is complete in device memory before any stream can be handed the pointer
+    if (bytes && cudaMemcpy(dev, host_data, bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(dev);
+        return nullptr;
+    }
+    g_table_bytes += bytes;
+    g_tables->emplace(h, CachedTable{k, dev});
+    return dev;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -9,15 +9,18 @@
 //     real (K', W') "image" [[Mr, Mi], [-Mi, Mr]] (4M complex product, no extra passes);
 //   * A tiles (128 rows x 16 k') arrive by TMA with the 128-byte swizzle; the coefficient image
 //     is pre-arranged in MMA fragment order, so it arrives by one 1-D bulk copy per stage;
-//   * 4 warps (one per SM sub-partition) own a 32 x (8*NT) accumulator tile each in registers
-//     and issue mma.sync m8n8k4 f64 (SASS DMMA.8x8x4; measured 16 clk issue interval per
-//     sub-partition, 26 clk latency, so one warp with >= 2 accumulators saturates its pipe);
-//     thread 0 doubles as the TMA producer, 3 chunks ahead, over a 4-stage full/empty mbarrier
-//     ring (a 5th warp would cap the kernel at 168 registers/thread and spill); 2 CTAs per SM
-//     so one CTA's epilogue overlaps the other's main loop;
+//   * one persistent CTA per SM, 12 warps: two MMA groups of 4 warps (one warp per SM sub-partition, a
+//     32 x (8*NT) accumulator tile each in registers) issue mma.sync m8n8k4 f64 (SASS DMMA.8x8x4; measured
+//     16 clk issue interval per sub-partition, 26 clk latency) on alternate tiles, each fed by its own TMA
+//     producer warp over its own full/empty mbarrier stage ring; the producer warp group donates registers
+//     (setmaxnreg 24 / 240); tile starts are ordered so one group's epilogue overlaps the other's main loop
+//     (details above quarter_gemm_kernel);
 //   * the epilogue writes the new index as the slowest axis (or any 2-level strided address).
 #include <stdlib.h>
 
+#include <mutex>
+#include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "common.cuh"
@@ -791,10 +794,11 @@ EncodeTiledFn get_encode_fn() {
 template <int NT, bool CO>
 int launch_variant(const CUtensorMap& map, const QuarterParams& p, cudaStream_t st) {
     constexpr int smem = RingConfig<NT>::kSmemBytes;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[kMaxDevices] = {false};  // the attribute belongs to the device's context
+    const int dev = qs_current_device();
+    if (!configured[dev]) {
         QS_CUDA(cudaFuncSetAttribute(quarter_gemm_kernel<NT, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
+        configured[dev] = true;
     }
     const int64_t total = p.tile_list ? (int64_t)p.n_listed : (int64_t)p.tiles_x * p.tiles_w;
     const int64_t resident = qs_sm_count();  // one persistent CTA per SM
@@ -823,10 +827,11 @@ int launch_nt(int NT, const CUtensorMap& map, const QuarterParams& p, cudaStream
 template <int NTC>
 int launch_split_variant(const CUtensorMap& map, const QuarterParams& p, cudaStream_t st) {
     constexpr int smem = SplitRing<NTC>::kSmemBytes;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[kMaxDevices] = {false};  // the attribute belongs to the device's context
+    const int dev = qs_current_device();
+    if (!configured[dev]) {
         QS_CUDA(cudaFuncSetAttribute(quarter_gemm_split_kernel<NTC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
+        configured[dev] = true;
     }
     const int64_t total = p.tile_list ? (int64_t)p.n_listed : (int64_t)p.tiles_x * p.tiles_w;
     const int64_t resident = qs_sm_count();
@@ -1005,6 +1010,83 @@ double plan_tile_lists(const Tiling& tl, int64_t X, int64_t x_inner, bool out_co
     return all ? (double)kept / (double)all : 1.0;
 }
 
+// The tile lists of a masked launch depend on the extents and the mask only, never on the data: they are planned on
+// the host once per (device, shape, mask), uploaded once and reused from device memory by every later call
+// (qs_table_cache_*), so a steady-state masked launch issues no host-to-device copy.
+struct PlannedLists {
+    const uint32_t* dev[2];
+    uint32_t count[2];
+    double fraction;
+};
+
+struct ListKey {
+    int tag, a_dtype, m_dtype, out_complex, kind, strict, device, pad;
+    int64_t X, x_inner, K, W, dh, mh, dl, ml, table_len;
+    uint64_t table_hash;
+};
+
+std::mutex g_lists_mutex;
+std::unordered_map<std::string, PlannedLists>* g_lists = nullptr;
+
+// Returns false when the device-side cache is full; the caller then stages `lists` through its workspace.
+bool planned_lists(const Tiling& tl, int a_dtype, int m_dtype, int64_t X, int64_t x_inner, int64_t K, int64_t W,
+                   bool out_complex, const QsTileMask* mask, const long long* host_xq_table, PlannedLists* out,
+                   std::vector<uint32_t> (&lists)[2]) {
+    ListKey key;
+    memset(&key, 0, sizeof(key));
+    key.tag = 0x715;
+    key.a_dtype = a_dtype;
+    key.m_dtype = m_dtype;
+    key.out_complex = out_complex;
+    key.device = qs_current_device();
+    key.X = X;
+    key.x_inner = x_inner;
+    key.K = K;
+    key.W = W;
+    if (host_xq_table) {
+        key.table_len = qs_ceil_div(X, x_inner);
+        key.table_hash = qs_hash_bytes(host_xq_table, (size_t)key.table_len * sizeof(long long), 17);
+    } else {
+        key.kind = mask->kind;
+        key.strict = mask->strict;
+        key.dh = mask->dh;
+        key.mh = mask->mh;
+        key.dl = mask->dl;
+        key.ml = mask->ml;
+    }
+    const std::string k(reinterpret_cast<const char*>(&key), sizeof(key));
+    {
+        std::lock_guard<std::mutex> lock(g_lists_mutex);
+        if (g_lists) {
+            auto it = g_lists->find(k);
+            if (it != g_lists->end()) {
+                *out = it->second;
+                return true;
+            }
+        }
+    }
+    PlannedLists pl;
+    memset(&pl, 0, sizeof(pl));
+    pl.fraction = plan_tile_lists(tl, X, x_inner, out_complex, mask, host_xq_table, lists);
+    for (int gi = 0; gi < tl.ngroups; ++gi) {
+        pl.count[gi] = (uint32_t)lists[gi].size();
+        if (lists[gi].empty()) continue;
+        ListKey gk = key;
+        gk.pad = gi + 1;
+        pl.dev[gi] = static_cast<const uint32_t*>(
+            qs_table_cache_put(&gk, sizeof(gk), lists[gi].data(), lists[gi].size() * sizeof(uint32_t)));
+        if (!pl.dev[gi]) {
+            out->fraction = pl.fraction;
+            return false;
+        }
+    }
+    std::lock_guard<std::mutex> lock(g_lists_mutex);
+    if (!g_lists) g_lists = new std::unordered_map<std::string, PlannedLists>();
+    (*g_lists)[k] = pl;
+    *out = pl;
+    return true;
+}
+
 int quarter_launch(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda, const void* image, int m_dtype,
                    int64_t W, void* out, void* const* out_table, int64_t n_dest, int64_t x_inner, int64_t x_mid,
                    int64_t sx0, int64_t sx1, int64_t sx2, int64_t w_inner, int64_t sw0, int64_t sw1, int64_t w_deal,
@@ -1067,9 +1149,14 @@ int quarter_launch(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda
     QS_REQUIRE(!(xq_table || xr_table) || x_mid == 0xFFFFFFFFLL,
                "qs_quarter_transform: row-offset tables need the two-level row split");
     const bool masked = (mask && mask->kind) || host_xq_table;
+    PlannedLists cached;
+    memset(&cached, 0, sizeof(cached));
+    bool lists_cached = false;
     if (masked) {
         QS_REQUIRE(list_ws && w_deal == 1 && n_dest == 0, "qs_quarter_transform: a masked launch needs list space");
-        wanted_fraction = plan_tile_lists(tl, X, x_inner, out_complex, mask, host_xq_table, lists);
+        lists_cached = planned_lists(tl, a_dtype, m_dtype, X, x_inner, K, W, out_complex, mask, host_xq_table, &cached,
+                                     lists);
+        wanted_fraction = cached.fraction;
     }
     int span = -1;
     // issued flops; the split variant's Wp counts complex columns, each fed by Kp real multiply-adds per row
@@ -1079,9 +1166,14 @@ int quarter_launch(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda
         const TileGroup& gr = tl.group[gi];
         QuarterParams p;
         memset(&p, 0, sizeof(p));
-        if (masked) {
+        if (masked && lists_cached) {
+            if (cached.count[gi] == 0) continue;
+            p.tile_list = cached.dev[gi];
+            p.n_listed = cached.count[gi];
+        } else if (masked) {
+            // table cache full: stage this call's list through the workspace (pageable source: the runtime
+            // stages the bytes before returning)
             if (lists[gi].empty()) continue;
-            // pageable source: the runtime stages the bytes before returning
             QS_CUDA(cudaMemcpyAsync(list_dev, lists[gi].data(), lists[gi].size() * sizeof(uint32_t),
                                     cudaMemcpyHostToDevice, st));
             p.tile_list = list_dev;

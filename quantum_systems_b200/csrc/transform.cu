@@ -174,22 +174,33 @@ extern "C" int qs_transform_two_body_symmetric(const void* u, int u_dtype, const
     // Wanted pairs (r, s), r < s or r <= s, numbered row-major: T3 is kept PACKED by pair, T3p[q, pair, a], so that
     // step 4 is a dense GEMM over m * npairs rows (in the plain layout its 128-row tiles would span the whole
     // range of s and none could be skipped).
-    std::vector<long long> host_tables((size_t)(M * M + M * (M + 1) / 2));
-    long long* slot_of_rs = host_tables.data();        // [r * M + s] -> pair * P, or -1 for an unwanted pair
-    long long* rs_of_pair = host_tables.data() + M * M;  // [pair] -> r * M + s
-    int64_t npairs = 0;
-    for (int64_t r = 0; r < M; ++r)
-        for (int64_t sI = 0; sI < M; ++sI) {
-            const bool wanted = strict ? r < sI : r <= sI;
-            slot_of_rs[r * M + sI] = wanted ? npairs * P : -1;
-            if (wanted) rs_of_pair[npairs++] = r * M + sI;
-        }
+    // The tables depend on (M, P, strict) only: built once per device and kept in device memory (qs_table_cache_*).
+    const int64_t npairs = strict ? M * (M - 1) / 2 : M * (M + 1) / 2;
     if (npairs == 0) return qs_mirror_fill(out, td, M, symmetry, stream);  // m = 1, antisymmetric: everything is zero
-    // pageable source: staged by the runtime before the call returns
-    QS_CUDA(cudaMemcpyAsync(tables, host_tables.data(), host_tables.size() * sizeof(long long), cudaMemcpyHostToDevice,
-                            static_cast<cudaStream_t>(stream)));
-    const long long* dev_slot_of_rs = tables;
-    const long long* dev_rs_of_pair = tables + M * M;
+    struct { int64_t tag, M, P, strict; } table_key = {0x7ab1e, M, P, strict};
+    const long long* dev_tables = static_cast<const long long*>(qs_table_cache_get(&table_key, sizeof(table_key)));
+    if (!dev_tables) {
+        std::vector<long long> host_tables((size_t)(M * M + M * (M + 1) / 2));
+        long long* slot_of_rs = host_tables.data();          // [r * M + s] -> pair * P, or -1 for an unwanted pair
+        long long* rs_of_pair = host_tables.data() + M * M;  // [pair] -> r * M + s
+        int64_t pair = 0;
+        for (int64_t r = 0; r < M; ++r)
+            for (int64_t sI = 0; sI < M; ++sI) {
+                const bool wanted = strict ? r < sI : r <= sI;
+                slot_of_rs[r * M + sI] = wanted ? pair * P : -1;
+                if (wanted) rs_of_pair[pair++] = r * M + sI;
+            }
+        dev_tables = static_cast<const long long*>(
+            qs_table_cache_put(&table_key, sizeof(table_key), host_tables.data(), host_tables.size() * sizeof(long long)));
+        if (!dev_tables) {
+            // cache full: stage through the workspace (pageable source: staged by the runtime before the call returns)
+            QS_CUDA(cudaMemcpyAsync(tables, host_tables.data(), host_tables.size() * sizeof(long long),
+                                    cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
+            dev_tables = tables;
+        }
+    }
+    const long long* dev_slot_of_rs = dev_tables;
+    const long long* dev_rs_of_pair = dev_tables + M * M;
     // step 2: rows (s, a, b), new column r -- tiles wanted iff they hold some r < s;  T2[r, s, a, b]
     const QsTileMask m2 = {1, strict, 1, 1, N * N, M};
     if ((rc = masked_rotated_quarter(bufA, td, M * N * N, N, P, img2, c_dtype, M, bufB, N, P, &m2, lists, stream))) return rc;

@@ -76,12 +76,18 @@ def _construct_fock(system, h, u, f, spatial):
         import numpy
 
         idx = numpy.arange(n_occ)
-        # advanced indices split by a slice put the gathered axis first: (n_occ, n, n)
+        # qs_fock_gathered reads both blocks as (n_occ, n, n), ordered [i, p, q].  Advanced indices split by a
+        # slice put the gathered axis first: u[:, idx, :, idx][i, p, q] = u[p, i, q, i].  ADJACENT advanced
+        # indices stay in place, u[:, idx, idx, :][p, i, q] = u[p, i, i, q], so that block is transposed.
         direct = numpy.ascontiguousarray(u[:, idx, :, idx])
-        exchange = numpy.ascontiguousarray(u[:, idx, idx, :]) if spatial else None
+        exchange = numpy.ascontiguousarray(u[:, idx, idx, :].transpose(1, 0, 2)) if spatial else None
         h_dev = _arrays.to_device(h)
         if h_dev.dtype == torch.float64 and numpy.iscomplexobj(direct):
-            raise TypeError("complex u cannot be accumulated into a real Fock matrix")
+            # the reference's `f.fill(0); f += h; f += ...` accumulates a real h into a caller's complex f
+            if f is not None and (f.is_complex() if isinstance(f, torch.Tensor) else numpy.iscomplexobj(f)):
+                h_dev = h_dev.to(torch.complex128)
+            else:
+                raise TypeError("complex u cannot be accumulated into a real Fock matrix")
         out = ops.fock_gathered(
             h_dev, _arrays.to_device(direct), _arrays.to_device(exchange) if spatial else None, n_occ,
             2.0 if spatial else 1.0, -1.0 if spatial else 0.0,

@@ -13,6 +13,19 @@ from . import _arrays, ops, potentials
 from .basis_set import BasisSet
 
 
+def grid_orbitals(l, grid_length, num_grid_points, potential):
+    """Host part of the ODQD recipe (one_dim_qd.py:258-266): the grid, and the ``l`` lowest eigenpairs of the
+    finite-difference Hamiltonian on the interior points.  Returns ``(grid, eps, C)`` with ``C`` of shape
+    ``(num_grid_points - 2, l)``; O(G l) work on the host."""
+    grid = _numpy.linspace(-grid_length, grid_length, num_grid_points)
+    inner = grid[1:-1]
+    dx = grid[1] - grid[0]
+    diagonal = 1.0 / (dx**2) + potential(inner)
+    off_diagonal = -1.0 / (2 * dx**2) * _numpy.ones(num_grid_points - 3)
+    eps, C = scipy.linalg.eigh_tridiagonal(diagonal, off_diagonal, select="i", select_range=(0, l - 1))
+    return grid, eps, C
+
+
 class ODQD(BasisSet):
     """Create a 1-D quantum-dot basis of the ``l`` lowest eigenfunctions of ``potential`` on
     ``linspace(-grid_length, grid_length, num_grid_points)``.
@@ -62,9 +75,7 @@ class ODQD(BasisSet):
         dx = self.grid[1] - self.grid[0]
 
         # finite-difference Hamiltonian on the interior points; l lowest eigenpairs (host, O(G l))
-        diagonal = 1.0 / (dx**2) + self.potential(inner)
-        off_diagonal = -1.0 / (2 * dx**2) * _numpy.ones(self.num_grid_points - 3)
-        eps, C = scipy.linalg.eigh_tridiagonal(diagonal, off_diagonal, select="i", select_range=(0, self.l - 1))
+        _, eps, C = grid_orbitals(self.l, self.grid_length, self.num_grid_points, self.potential)
         self.eigen_energies = eps
 
         spf = _numpy.zeros((self.l, self.num_grid_points), dtype=_numpy.complex128)

@@ -74,9 +74,21 @@ def real_coefficients_if_exact(u_is_complex, C, C_tilde):
     skipped products are exact zeros).  Only when ``u`` is complex, so the result dtype does not change."""
     if not (u_is_complex and C.is_complex()):
         return C, C_tilde
-    if bool(torch.any(C.imag != 0)) or (C_tilde is not None and bool(torch.any(C_tilde.imag != 0))):
+    if _has_imaginary_part(C) or (C_tilde is not None and _has_imaginary_part(C_tilde)):
         return C, C_tilde
     return C.real.contiguous(), (C_tilde.real.contiguous() if C_tilde is not None else None)
+
+
+def _has_imaginary_part(M):
+    """``any(M.imag != 0)`` -- a device reduction read back by the host, i.e. a stream synchronisation.  The answer
+    is remembered on the tensor object together with torch's in-place version counter, so a chain of basis changes
+    with the same coefficient tensor synchronises once."""
+    tag = getattr(M, "_qs_has_imag", None)
+    if tag is not None and tag[1] == M._version:
+        return tag[0]
+    answer = bool(torch.any(M.imag != 0))
+    M._qs_has_imag = (answer, M._version)
+    return answer
 
 
 # below this extent the symmetry test costs more than the tiles it saves
@@ -85,6 +97,21 @@ SYMMETRY_MIN_N = 48
 EXPLOIT_SYMMETRY = True
 ANTISYMMETRIC_LAST_PAIR = 1  # u[p,q,r,s] = -u[p,q,s,r]
 PARTICLE_EXCHANGE = 2        # u[p,q,r,s] =  u[q,p,s,r]
+
+
+def _tag_symmetry(t, kind):
+    """Remember on the tensor object that the library itself has just made ``t`` EXACTLY (anti-)symmetric (mirror
+    fill, fused anti-symmetrisation).  The tag carries torch's in-place version counter: any later in-place
+    modification through torch bumps ``t._version`` and voids it, and a new tensor (copy, host round trip, the
+    ``u`` setter of a host array) never has it -- then the device-side test runs again."""
+    t._qs_symmetry = (int(kind), t._version)
+    return t
+
+
+def proven_symmetry(t):
+    """The symmetry kind the library has proven for this very tensor object, or 0."""
+    tag = getattr(t, "_qs_symmetry", None)
+    return tag[0] if tag is not None and tag[1] == t._version else 0
 
 
 def two_body_symmetry(u, first_match=False):
@@ -119,11 +146,15 @@ def transform_two_body(u, C, C_tilde=None, symmetry=None):
     if symmetry is None:
         symmetry = 0
         if EXPLOIT_SYMMETRY and min(n, m) >= SYMMETRY_MIN_N:
-            flags = two_body_symmetry(u, first_match=True)
-            symmetry = (
-                ANTISYMMETRIC_LAST_PAIR if flags & ANTISYMMETRIC_LAST_PAIR
-                else PARTICLE_EXCHANGE if flags & PARTICLE_EXCHANGE else 0
-            )
+            # a tensor this library has itself made exactly (anti-)symmetric is not tested again: no pass over u,
+            # no host synchronisation in a chain of basis changes
+            symmetry = proven_symmetry(u)
+            if not symmetry:
+                flags = two_body_symmetry(u, first_match=True)
+                symmetry = (
+                    ANTISYMMETRIC_LAST_PAIR if flags & ANTISYMMETRIC_LAST_PAIR
+                    else PARTICLE_EXCHANGE if flags & PARTICLE_EXCHANGE else 0
+                )
     out = torch.empty((m, m, m, m), dtype=_result_dtype(u, C), device=u.device)
     nbytes = ctypes.c_int64(0)
     _native.call("qs_transform_two_body_workspace_bytes", n, m, _code(u), _code(C), ctypes.byref(nbytes))
@@ -133,6 +164,8 @@ def transform_two_body(u, C, C_tilde=None, symmetry=None):
         _ptr(out), ws, nbytes.value, _stream(),
     )
     owner.record_stream(torch.cuda.current_stream())
+    if symmetry:
+        _tag_symmetry(out, symmetry)  # the mirror fill has made the result exactly (anti-)symmetric
     return out
 
 
@@ -212,6 +245,8 @@ def add_spin_two_body(u, anti_symmetrize=False, out_dtype=None, planes=None, out
         "qs_add_spin_two_body", base, _code(u), l, _ptr(out), _DTYPES[out_dtype], int(bool(anti_symmetrize)), p0,
         p1, _stream(),
     )
+    if anti_symmetrize and planes is None:
+        _tag_symmetry(out, ANTISYMMETRIC_LAST_PAIR)  # a - b and b - a are exact negatives
     return out
 
 
@@ -224,6 +259,8 @@ def anti_symmetrize(u):
     out = torch.empty_like(u)
     # `u` may be a leading-index shard: planes [0, u.shape[0]) of the local block
     _native.call("qs_anti_symmetrize", _ptr(u), _code(u), n, _ptr(out), 0, u.shape[0], _stream())
+    if u.shape[0] == n:
+        _tag_symmetry(out, ANTISYMMETRIC_LAST_PAIR)
     return out
 
 

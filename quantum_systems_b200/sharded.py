@@ -31,6 +31,7 @@ check the schedule under gloo without a GPU.
 """
 
 import ctypes
+import weakref
 
 import torch
 
@@ -50,6 +51,8 @@ def block_partition(n, world):
 
 # below this extent the symmetry test costs more than the tiles it saves
 SYMMETRY_MIN_N = 48
+# False: `transform_two_body_sharded(symmetry=None)` never tests for anti-symmetry and runs the four full quarter steps
+EXPLOIT_SYMMETRY = True
 
 
 def cyclic_wanted(r, s, m):
@@ -335,6 +338,19 @@ class ProcessContext:
         )
 
 
+def _owners(ctx):
+    return ctx.__dict__.setdefault("_buffer_owners", {})
+
+
+def _recycle(ctx, buffers, keep=None):
+    """``buffers`` are about to be overwritten: the handle that still points at them (if any, and unless it is
+    ``keep``) becomes invalid instead of silently showing the new contents."""
+    ref = _owners(ctx).pop(id(buffers), None)
+    old = ref() if ref is not None else None
+    if old is not None and old is not keep:
+        old._buffers = None
+
+
 def _cached(ctx, tag, numels, dtype):
     cache = ctx.__dict__.setdefault("_shared_cache", {})
     key = (tag, tuple(int(x) for x in numels), dtype)
@@ -358,9 +374,27 @@ class ShardedTwoBody:
         self.ctx = ctx
         self.n = n
         self.dtype = dtype
-        self.buffers = buffers  # {rank: [buffer of every rank]}
+        self._buffers = buffers  # {rank: [buffer of every rank]}
         self.spare = spare
         self.block, self.offsets = block_partition(n, ctx.world)
+        # True once the library itself has made the tensor EXACTLY anti-symmetric in its last pair (fused spin
+        # doubling, cyclic mirror fill): the transform then skips the device-side test (a full read of u, a host
+        # synchronisation and an all-reduce per call).  Writing through ``local()`` voids it: set it to False.
+        self.proven_antisymmetric = False
+        # who currently owns a buffer set: a transform that recycles the set invalidates that handle
+        _owners(ctx)[id(buffers)] = weakref.ref(self)
+
+    @property
+    def buffers(self):
+        """The peer-visible slabs.  Raises once a later transform has recycled them (the reference's
+        ``change_basis`` returns fresh arrays; here a tensor replaced TWO calls earlier donates its memory --
+        ``copy()`` keeps an old tensor alive)."""
+        if self._buffers is None:
+            raise RuntimeError(
+                "this ShardedTwoBody was recycled: a later change_basis wrote its result into these buffers "
+                "(ping-pong); take .copy() before the second transform to keep an old tensor"
+            )
+        return self._buffers
 
     @property
     def shape(self):
@@ -457,7 +491,37 @@ class ShardedTwoBody:
                 mine = self.buffers[r][r]
                 self.ctx.engine.scale_add(mine, other.buffers[r][r] if other is not None else None, count, alpha, beta,
                                           mine)
+        self.proven_antisymmetric = self.proven_antisymmetric and (other is None or other.proven_antisymmetric)
         return self
+
+    def successor(self):
+        """A handle over this tensor's SPARE buffers whose own spare is this tensor's memory, for a caller that is
+        done with this tensor and wants to build the next one in place (``from_spatial_planes(..., into=...)`` of
+        the next spatial tensor) without new peer allocations.  This handle stays valid until a transform of the
+        successor recycles its buffers."""
+        if self.spare is None:
+            raise RuntimeError("this ShardedTwoBody has no spare buffer set")
+        _recycle(self.ctx, self.spare, keep=self)
+        return ShardedTwoBody(self.ctx, self.n, self.dtype, self.spare, self.buffers)
+
+    def scaled(self, alpha, other=None, beta=0.0):
+        """A NEW sharded tensor ``alpha u + beta other`` in one pass per shard (``qs_scale_add``), no
+        communication: ``u_t = u_0 + f(t) u`` of reference system.py:203-215 / operator.py:182-196."""
+        if other is not None and (other.n != self.n or other.dtype != self.dtype):
+            raise ValueError("operands must share extent and dtype")
+        alpha, beta = complex(alpha), complex(beta)
+        if self.dtype != torch.complex128 and (alpha.imag != 0 or beta.imag != 0):
+            raise TypeError("complex factor on a real sharded tensor")
+        new = ShardedTwoBody.empty(self.ctx, self.n, self.dtype, with_spare=False)
+        for r in self.ctx.local_ranks:
+            p0, p1 = self.planes(r)
+            count = (p1 - p0) * self.n**3
+            if count:
+                self.ctx.engine.scale_add(self.buffers[r][r], other.buffers[r][r] if other is not None else None,
+                                          count, alpha, beta, new.buffers[r][r])
+        self.ctx.barrier()
+        new.proven_antisymmetric = self.proven_antisymmetric and (other is None or other.proven_antisymmetric)
+        return new
 
     def copy(self):
         """A new sharded tensor (own buffers, no spare) with the same contents."""
@@ -468,6 +532,7 @@ class ShardedTwoBody:
             if count:
                 self.ctx.engine.scale_add(self.buffers[r][r], None, count, 1.0, 0.0, new.buffers[r][r])
         self.ctx.barrier()
+        new.proven_antisymmetric = self.proven_antisymmetric
         return new
 
     def occupied_traces(self, h, n_occ):
@@ -591,6 +656,13 @@ class _RankTransform:
         import numpy
 
         m, R, P = self.m, self.R, self.P
+        # shape-dependent only: built and uploaded once per (rank, m, world, P), then reused by every transform
+        cache = self.ctx.__dict__.setdefault("_pair_tables", {})
+        key = (self.rank, m, self.ctx.world, P)
+        if key in cache:
+            (self.npairs, self.slot_of_rs, self.rs_of_pair, self.slot_of_rs_dev, self.rs_of_pair_dev) = cache[key]
+            return
+        self.slot_of_rs_dev = self.rs_of_pair_dev = None
         r = self.r_off[self.rank] + numpy.arange(R, dtype=numpy.int64)[:, None]
         sI = numpy.arange(m, dtype=numpy.int64)[None, :]
         wanted = cyclic_wanted(r, sI, m)
@@ -602,6 +674,7 @@ class _RankTransform:
         if self.npairs:
             self.slot_of_rs_dev = self.engine.index_table(self.slot_of_rs)
             self.rs_of_pair_dev = self.engine.index_table(self.rs_of_pair)
+        cache[key] = (self.npairs, self.slot_of_rs, self.rs_of_pair, self.slot_of_rs_dev, self.rs_of_pair_dev)
 
     def step3_pairs(self, recv_local):
         """T3p[q, pair(r_loc, s), a] = sum_b T2[r_loc, s, a, b] C~[q, b] for the wanted pairs only."""
@@ -665,7 +738,8 @@ def transform_two_body_sharded(u, C, C_tilde=None, symmetry=None):
     if n != u.n:
         raise ValueError(f"C has {n} rows but u has {u.n} orbitals")
     if symmetry is None:
-        symmetry = 1 if (ctx.exchange == "peer" and min(n, m) >= SYMMETRY_MIN_N and is_antisymmetric_last_pair(u)) else 0
+        symmetry = 1 if (EXPLOIT_SYMMETRY and ctx.exchange == "peer" and min(n, m) >= SYMMETRY_MIN_N
+                         and (u.proven_antisymmetric or is_antisymmetric_last_pair(u))) else 0
     if symmetry and ctx.exchange != "peer":
         raise ValueError("the symmetry-aware sharded transform needs the peer exchange")
     work = {r: _RankTransform(ctx, r, n, m, u.dtype, C.dtype) for r in ctx.local_ranks}
@@ -679,6 +753,7 @@ def transform_two_body_sharded(u, C, C_tilde=None, symmetry=None):
         out_numels = [any_w.out_numel(r) for r in range(ctx.world)]
         if u.spare is not None and u.dtype == t_dtype and m == n:
             out = u.spare  # ping-pong: reuse the buffers of the tensor replaced one call earlier
+            _recycle(ctx, out, keep=u)  # a caller still holding that older tensor gets an error, not new data
         else:
             out = ctx.shared_empty(out_numels, t_dtype)
         ctx.barrier()  # every rank is done with whatever it last read from these buffers
@@ -699,7 +774,9 @@ def transform_two_body_sharded(u, C, C_tilde=None, symmetry=None):
             for r, w in work.items():
                 ctx.engine.cyclic_fill(out[r][r], m, w.R)  # the other half of every local plane: -u'[p,q,s,r]
         spare = u.buffers if (u.dtype == t_dtype and m == n) else None
-        return ShardedTwoBody(ctx, m, t_dtype, out, spare)
+        result = ShardedTwoBody(ctx, m, t_dtype, out, spare)
+        result.proven_antisymmetric = bool(symmetry)  # the cyclic fill wrote exact negatives and a zero diagonal
+        return result
 
     # collective schedule (one rank per process)
     (r, w), = work.items()
@@ -800,12 +877,14 @@ class ShardedBasisSet:
                 ops.add_spin_two_body(u_dev, anti_symmetrize=anti_symmetrize, out_dtype=out_dtype, planes=(p0, p1),
                                       out=u.local(r))
         ctx.barrier()
+        u.proven_antisymmetric = bool(anti_symmetrize)  # the fused pass writes a - b and b - a: exact negatives
         h2 = ops.add_spin_one_body(_arrays.to_device(h), out_dtype=out_dtype)
         s2 = ops.add_spin_one_body(_arrays.to_device(s), out_dtype=out_dtype)
         return cls(ctx, n, h2, s2, u, includes_spin=True, anti_symmetrized_u=bool(anti_symmetrize))
 
     @classmethod
-    def from_spatial_planes(cls, ctx, h, s, l, spatial_planes, anti_symmetrize=True, out_dtype=torch.complex128):
+    def from_spatial_planes(cls, ctx, h, s, l, spatial_planes, anti_symmetrize=True, out_dtype=torch.complex128,
+                            into=None):
         """Like :meth:`from_spatial`, but no rank ever holds the whole spatial tensor: ``spatial_planes(p0, p1)``
         returns (builds) the planes ``u_spatial[p0:p1]`` as a ``(p1 - p0, l, l, l)`` device tensor, and every rank
         asks only for the planes behind its own spin-orbital planes ``P = 2p + sigma``.  With
@@ -815,7 +894,9 @@ class ShardedBasisSet:
         from . import _arrays, ops
 
         n = 2 * l
-        u = ShardedTwoBody.empty(ctx, n, out_dtype)
+        u = into if into is not None else ShardedTwoBody.empty(ctx, n, out_dtype)
+        if u.n != n or u.dtype != out_dtype:
+            raise ValueError("`into` must be a ShardedTwoBody of extent 2 l and the requested dtype")
         for r in ctx.local_ranks:
             p0, p1 = u.planes(r)
             if p1 > p0:
@@ -826,9 +907,32 @@ class ShardedBasisSet:
                 ops.add_spin_two_body(slab, anti_symmetrize=anti_symmetrize, out_dtype=out_dtype, planes=(p0, p1),
                                       out=u.local(r), first_spatial_plane=sp0)
         ctx.barrier()
+        u.proven_antisymmetric = bool(anti_symmetrize)  # the fused pass writes a - b and b - a: exact negatives
         h2 = ops.add_spin_one_body(_arrays.to_device(h), out_dtype=out_dtype)
         s2 = ops.add_spin_one_body(_arrays.to_device(s), out_dtype=out_dtype)
         return cls(ctx, n, h2, s2, u, includes_spin=True, anti_symmetrized_u=bool(anti_symmetrize))
+
+    @classmethod
+    def from_odqd(cls, ctx, l, grid_length, num_grid_points, a=0.25, alpha=1.0, potential=None,
+                  anti_symmetrize=True, out_dtype=torch.complex128, into=None):
+        """The sharded counterpart of ``GeneralOrbitalSystem(n, ODQD(l, grid_length, num_grid_points, ...))``
+        (reference one_dim_qd.py:258-289 -> general_orbital_system.py:39-53 -> basis_set.py:530-636): the O(G l)
+        eigenproblem on the host of every rank (replicated, microseconds to seconds), then the grid Coulomb build,
+        spin doubling and anti-symmetrisation of this rank's planes only.  The eigenvectors are kept as
+        ``grid_coefficients`` (G', l) and the interior grid as ``inner_grid``."""
+        from . import potentials
+        from .odqd import grid_orbitals
+
+        potential = potentials.HOPotential(0.25) if potential is None else potential
+        grid, eps, Cg = grid_orbitals(l, grid_length, num_grid_points, potential)
+        import numpy
+
+        basis = cls.from_spatial_planes(
+            ctx, numpy.diag(eps), numpy.eye(l), l, odqd_spatial_planes(Cg, grid[1:-1], alpha, a),
+            anti_symmetrize=anti_symmetrize, out_dtype=out_dtype, into=into,
+        )
+        basis.grid_coefficients, basis.inner_grid = Cg, grid[1:-1]
+        return basis
 
     def change_basis(self, C, C_tilde=None):
         """``h, s <- C~ X C`` on every rank (replicated, O(n^3)); ``u`` through the sharded transform."""

@@ -11,6 +11,49 @@ import types
 import typing
 
 
+def _is_scalar(x):
+    return isinstance(x, (int, float, complex)) or getattr(x, "ndim", None) == 0
+
+
+def _zeros_like(module, a):
+    from .sharded import ShardedTwoBody
+
+    if isinstance(a, ShardedTwoBody):
+        return a.scaled(0.0)
+    return module.zeros_like(a)
+
+
+def scaled_sum(module, terms):
+    """``sum_k w_k X_k`` for ``terms = [(w_k, X_k), ...]`` of equally shaped arrays, with ``qs_scale_add``: the
+    first two terms in one pass, every further term one in-place pass.  ``X_k`` may be CUDA tensors, host arrays
+    (staged; the result is returned in the storage of ``module``) or ``ShardedTwoBody`` handles (shard-local, no
+    communication).  Mixed real / complex operands and complex weights give a complex128 result."""
+    import torch
+
+    from . import _arrays, ops
+    from .sharded import ShardedTwoBody
+
+    (w0, x0), rest = terms[0], terms[1:]
+    if isinstance(x0, ShardedTwoBody):
+        acc = x0.scaled(w0, rest[0][1], rest[0][0]) if rest else x0.scaled(w0)
+        for w, x in rest[1:]:
+            acc.axpby_(1.0, x, w)
+        return acc
+    device_in = isinstance(x0, torch.Tensor) and x0.is_cuda
+    xs = [_arrays.to_device(x) for _, x in terms]
+    ws = [w for w, _ in terms]
+    if len(xs) == 1:
+        acc = ops.scale_add(xs[0], ws[0])
+    else:
+        acc = ops.scale_add(xs[0], ws[0], xs[1], ws[1])
+        for w, x in zip(ws[2:], xs[2:]):
+            if x.dtype != acc.dtype or complex(w).imag != 0:
+                acc = ops.scale_add(acc, 1.0, x, w)  # promotion: a fresh complex result
+            else:
+                ops.scale_add(acc, 1.0, x, w, out=acc)
+    return acc if device_in and not _arrays.is_host_module(module) else _arrays.to_module(acc, module)
+
+
 class QuantumSystem(metaclass=abc.ABCMeta):
     """Abstract base: ``n`` occupied basis functions out of ``basis_set.l`` (system.py:6-30)."""
 
@@ -126,16 +169,35 @@ class QuantumSystem(metaclass=abc.ABCMeta):
         return any(op.is_two_body_operator for op in self._time_evolution_operator)
 
     def h_t(self, current_time):
-        h_0 = self._basis_set.h if self._add_h_0 else self.np.zeros_like(self._basis_set.h)
-        if not self.has_one_body_time_evolution_operator:
-            return h_0
-        return h_0 + sum(op.h_t(current_time) for op in self._time_evolution_operator)
+        """``h_0 + sum_op h_op(t)`` (system.py:189-201), accumulated by ``qs_scale_add``."""
+        return self._hamiltonian_part(
+            self._basis_set.h, self._add_h_0, self.has_one_body_time_evolution_operator, "h_t", current_time
+        )
 
     def u_t(self, current_time):
-        u_0 = self._basis_set.u if self._add_u_0 else self.np.zeros_like(self._basis_set.u)
-        if not self.has_two_body_time_evolution_operator:
-            return u_0
-        return u_0 + sum(op.u_t(current_time) for op in self._time_evolution_operator)
+        """``u_0 + sum_op u_op(t)`` (system.py:203-215).  Every term costs one ``qs_scale_add`` pass over the n^4
+        elements -- ``u_0 + f(t) u`` of an adiabatic switching a single one -- in HBM-resident, host and sharded
+        storage alike."""
+        return self._hamiltonian_part(
+            self._basis_set.u, self._add_u_0, self.has_two_body_time_evolution_operator, "u_t", current_time
+        )
+
+    def _hamiltonian_part(self, base, add_base, any_operator, method, current_time):
+        if not any_operator:
+            return base if add_base else _zeros_like(self.np, base)
+        terms = [(1.0, base)] if add_base else []
+        constant = 0
+        for op in self._time_evolution_operator:
+            scaled = getattr(op, method + "_scaled", None)
+            weight, operand = scaled(current_time) if scaled is not None else (1.0, getattr(op, method)(current_time))
+            if _is_scalar(operand):  # the base class contributes the number 0 (operator.py:66, :84)
+                constant = constant + weight * operand
+            else:
+                terms.append((weight, operand))
+        if not terms:
+            return _zeros_like(self.np, base) + constant
+        out = scaled_sum(self.np, terms)
+        return out if _is_scalar(constant) and constant == 0 else out + constant
 
     def transform_one_body_elements(self, h, C, C_tilde=None):
         return self._basis_set.transform_one_body_elements(h, C, np=self.np, C_tilde=C_tilde)

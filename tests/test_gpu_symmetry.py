@@ -101,3 +101,82 @@ def test_symmetry_is_preserved_through_a_gos_change_basis():
     assert ops.two_body_symmetry(gos.u) & 1
     f = gos.construct_fock_matrix(gos.h, gos.u)
     assert_close_scaled(f.cpu().numpy(), oracle.construct_fock_matrix_general(ref["h"], ref["u"], 4))
+
+
+def test_library_made_symmetry_is_tagged_and_the_tag_dies_with_the_data():
+    """A tensor the library itself has just made exactly (anti-)symmetric -- fused spin doubling, anti_symmetrize,
+    a symmetry-aware transform -- is not tested again by the next transform (no pass over u, no host sync); any
+    in-place change through torch, and any new tensor, loses the tag, and then the exact test runs again."""
+    from quantum_systems_b200 import ops
+
+    n = 48
+    rng = np.random.default_rng(5)
+    plain = rng.standard_normal((n,) * 4)
+    u = dev(plain)
+    assert ops.proven_symmetry(u) == 0
+    anti = ops.anti_symmetrize(u)
+    assert ops.proven_symmetry(anti) == ops.ANTISYMMETRIC_LAST_PAIR
+    assert ops.two_body_symmetry(anti) & 1  # the tag tells the truth
+    spin = ops.add_spin_two_body(dev(plain[:24, :24, :24, :24]), anti_symmetrize=True)
+    assert ops.proven_symmetry(spin) == 1 and ops.two_body_symmetry(spin) & 1
+    assert ops.proven_symmetry(ops.add_spin_two_body(dev(plain[:24, :24, :24, :24]))) == 0
+    assert ops.proven_symmetry(ops.add_spin_two_body(dev(plain[:24, :24, :24, :24]), True, planes=(0, 10))) == 0
+
+    C = dev(np.linalg.qr(rng.standard_normal((n, n)))[0])
+    calls = []
+    real_test = ops.two_body_symmetry
+    ops.two_body_symmetry = lambda *a, **k: calls.append(1) or real_test(*a, **k)
+    try:
+        out = ops.transform_two_body(anti, C)          # tagged input: no detection
+        assert calls == [] and ops.proven_symmetry(out) == 1
+        out2 = ops.transform_two_body(out, C)          # a chain of basis changes never tests
+        assert calls == [] and ops.proven_symmetry(out2) == 1
+        expected = oracle.transform_two_body_elements(plain - plain.transpose(0, 1, 3, 2), C.cpu().numpy())
+        assert_close_scaled(out.cpu().numpy(), expected)
+        assert_close_scaled(out2.cpu().numpy(), oracle.transform_two_body_elements(expected, C.cpu().numpy()), rel=1e-11)
+        np.testing.assert_array_equal(out2.cpu().numpy(), -out2.cpu().numpy().transpose(0, 1, 3, 2))
+
+        out[3, 4, 5, 6] += 1.0                         # in-place change: the tag is void, the test runs and says no
+        assert ops.proven_symmetry(out) == 0
+        broken = ops.transform_two_body(out, C)
+        assert calls == [1] and ops.proven_symmetry(broken) == 0
+        expected_broken = oracle.transform_two_body_elements(out.cpu().numpy(), C.cpu().numpy())
+        assert_close_scaled(broken.cpu().numpy(), expected_broken)
+
+        clone = anti.clone()                           # a new tensor object is tested afresh (and passes)
+        assert ops.proven_symmetry(clone) == 0
+        again = ops.transform_two_body(clone, C)
+        assert calls == [1, 1] and ops.proven_symmetry(again) == 1
+    finally:
+        ops.two_body_symmetry = real_test
+
+
+def test_basis_set_chain_of_basis_changes_uses_the_tag():
+    """BasisSet(np=xp): the exchange symmetry of a user-supplied u is found once by the exact test; every later
+    change_basis of the chain trusts the library's own mirror fill."""
+    from quantum_systems_b200 import BasisSet, ops, xp
+
+    n = 48
+    rng = np.random.default_rng(9)
+    u = symmetric_input(rng, n, False, "exchange")
+    C = np.linalg.qr(rng.standard_normal((n, n)))[0]
+    bs = BasisSet(n, 1, np=xp)
+    bs.h, bs.s, bs.u = rng.standard_normal((n, n)), np.eye(n), u
+    calls = []
+    real_test = ops.two_body_symmetry
+    ops.two_body_symmetry = lambda *a, **k: calls.append(1) or real_test(*a, **k)
+    try:
+        bs.change_basis(xp.asarray(C))
+        bs.change_basis(xp.asarray(C))
+        bs.change_basis(xp.asarray(C))
+    finally:
+        ops.two_body_symmetry = real_test
+    assert calls == [1]
+    expected = u
+    for _ in range(3):
+        expected = oracle.transform_two_body_elements(expected, C)
+    assert_close_scaled(bs.u.cpu().numpy(), expected, rel=1e-11)
+    got = bs.u.cpu().numpy()
+    np.testing.assert_array_equal(got, got.transpose(1, 0, 3, 2))
+    bs.u = bs.u.cpu().numpy()  # a host round trip is a new tensor: tested again
+    assert ops.proven_symmetry(bs.u) == 0

@@ -99,6 +99,53 @@ def test_fock_and_reference_energy(module):
     assert_close_scaled(host(f_in), g["gos_fock"], rel=1e-13)
 
 
+@pytest.mark.parametrize("complex_u", [False, True])
+@pytest.mark.parametrize("particles", [4, 6])
+def test_spatial_fock_several_occupied_orbitals(module, particles, complex_u):
+    """Restricted Fock matrix with n_occ >= 2 in both storage modes (spatial_orbital_system.py:150-190).  With one
+    occupied orbital the [i,p,q] and [p,i,q] orders of the gathered exchange block coincide; with several they do
+    not, and the host path must hand the kernel u[p,i,i,q] ordered [i,p,q]."""
+    from quantum_systems_b200 import BasisSet, SpatialOrbitalSystem
+
+    rng = np.random.default_rng(particles + 10 * complex_u)
+    l = 7
+    u = rng.standard_normal((l,) * 4)
+    h = rng.standard_normal((l, l))
+    if complex_u:
+        u = u + 1j * rng.standard_normal((l,) * 4)
+        h = h + 1j * rng.standard_normal((l, l))
+    bs = BasisSet(l, 1, np=module)
+    bs.h, bs.s, bs.u = h.copy(), np.eye(l), u.copy()
+    spas = SpatialOrbitalSystem(particles, bs)
+    assert spas.n == particles // 2 >= 2
+    ref = oracle.construct_fock_matrix_spatial(h, u, particles // 2)
+    f = spas.construct_fock_matrix(spas.h, spas.u)
+    check_storage(f, module)
+    assert_close_scaled(host(f), ref, rel=1e-13)
+    energy = spas.compute_reference_energy()
+    np.testing.assert_allclose(energy, oracle.reference_energy_spatial(h, u, particles // 2), rtol=1e-12)
+
+
+def test_host_fock_real_h_complex_u_into_complex_f():
+    """`f.fill(0); f += h; f += ...` of the reference accepts a real h with a complex u when the caller supplies a
+    complex f (general_orbital_system.py:151-159); without f the real zeros_like(h) cannot take the sum."""
+    from quantum_systems_b200 import BasisSet, SpatialOrbitalSystem
+
+    rng = np.random.default_rng(5)
+    l = 6
+    u = rng.standard_normal((l,) * 4) + 1j * rng.standard_normal((l,) * 4)
+    h = rng.standard_normal((l, l))
+    bs = BasisSet(l, 1, np=np)
+    bs.h, bs.s, bs.u = h.copy(), np.eye(l), u.copy()
+    spas = SpatialOrbitalSystem(4, bs)
+    f = np.full((l, l), 7.0 + 0j)
+    ret = spas.construct_fock_matrix(spas.h, spas.u, f=f)
+    assert ret is f
+    assert_close_scaled(f, oracle.construct_fock_matrix_spatial(h.astype(complex), u, 2), rel=1e-13)
+    with pytest.raises(TypeError):
+        spas.construct_fock_matrix(spas.h, spas.u)
+
+
 def test_change_basis_rectangular(module):
     """tests/test_custom_system.py:38-68: 5 -> 8 spatial and 10 -> 8 spin-orbitals, atol = rtol = 1e-12."""
     from quantum_systems_b200 import SpatialOrbitalSystem

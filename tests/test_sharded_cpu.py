@@ -90,6 +90,31 @@ def test_emulated_peer_schedule_matches_oracle(world, n, m, u_complex, c_complex
         np.testing.assert_allclose(out2.gather().numpy(), expected2, rtol=1e-11, atol=1e-11 * np.abs(expected2).max())
 
 
+def test_recycled_handle_raises_instead_of_showing_new_data():
+    """A transform writes into the buffers of the tensor replaced one call earlier (ping-pong).  A caller that
+    still holds that older handle must get an error, not silently the newer tensor; copy() keeps data alive."""
+    from quantum_systems_b200 import sharded
+
+    n = 6
+    rng = np.random.default_rng(3)
+    u = rng.standard_normal((n,) * 4)
+    C = torch.from_numpy(np.linalg.qr(rng.standard_normal((n, n)))[0])
+    ctx = sharded.EmulatedContext(2, engine=NumpyEngine())
+    u0 = sharded.ShardedBasisSet.from_global(ctx, np.eye(n), np.eye(n), u).u
+    kept = u0.copy()
+    u1 = sharded.transform_two_body_sharded(u0, C)
+    np.testing.assert_array_equal(u0.gather().numpy(), u)  # one call later the input is still intact
+    u2 = sharded.transform_two_body_sharded(u1, C)  # writes into u0's buffers
+    with pytest.raises(RuntimeError, match="recycled"):
+        u0.gather()
+    with pytest.raises(RuntimeError, match="recycled"):
+        u0.local(0)
+    np.testing.assert_array_equal(kept.gather().numpy(), u)
+    expected = oracle.transform_two_body_elements(oracle.transform_two_body_elements(u, C.numpy()), C.numpy())
+    np.testing.assert_allclose(u2.gather().numpy(), expected, rtol=1e-11, atol=1e-11)
+    assert u1.gather().shape == (n,) * 4  # the tensor replaced ONE call earlier is still valid
+
+
 @pytest.mark.parametrize("world", [1, 2, 3, 5])
 @pytest.mark.parametrize("complex_", [False, True])
 def test_emulated_consumers_of_a_sharded_tensor(world, complex_):
@@ -117,6 +142,12 @@ def test_emulated_consumers_of_a_sharded_tensor(world, complex_):
     )
     scaled = basis.u.copy().axpby_(0.5)
     np.testing.assert_array_equal(scaled.gather().numpy(), 0.5 * u)
+    # u_t = u_0 + f(t) u on a sharded tensor (reference system.py:203-215): one new handle, shard-local passes
+    from quantum_systems_b200.system import scaled_sum
+
+    np.testing.assert_array_equal(basis.u.scaled(2.0, scaled, -1.0).gather().numpy(), 2.0 * u - 0.5 * u)
+    total = scaled_sum(None, [(1.0, basis.u), (0.25, basis.u), (-3.0, scaled)])
+    np.testing.assert_allclose(total.gather().numpy(), (1.25 - 1.5) * u, rtol=1e-15)
     np.testing.assert_array_equal(basis.u.gather().numpy(), u)  # the copy left the original alone
     combo = basis.u.copy().axpby_(2.0, scaled, -3.0)
     np.testing.assert_allclose(combo.gather().numpy(), 2.0 * u - 1.5 * u, rtol=1e-15)
