@@ -862,6 +862,7 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
         return
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
         line = run_sharded(args, torch, dist, lib, rank, world, local_rank)

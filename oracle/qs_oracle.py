@@ -21,6 +21,7 @@ All citations are relative to ``/root/reference/quantum_systems/``.
 
 import numpy as np
 import scipy.linalg
+import scipy.special
 
 
 # --------------------------------------------------------------------------------------------
@@ -318,6 +319,71 @@ def odqd_setup_basis(l, grid_length, num_grid_points, potential, a=0.25, alpha=1
         "s": np.eye(l),
         "u": odqd_coulomb_elements(C, grid, alpha, a),
         "position": position,
+    }
+
+
+def odho_functions(l, grid, omega):
+    """Harmonic-oscillator eigenfunctions on the grid, ``N_n exp(-omega x^2 / 2) H_n(sqrt(omega) x)`` with
+    ``N_n = (omega / pi)^(1/4) / sqrt(2^n n!)`` -- ``ODHO.ho_function`` / ``normalization``, one_dim_qd.py:136-148
+    (the reference evaluates ``scipy.special.hermite(n)``; same call here)."""
+    spf = np.zeros((l, grid.shape[0]))
+    for n in range(l):
+        norm = 1.0 / np.sqrt(2**n * scipy.special.factorial(n)) * (omega / np.pi) ** 0.25
+        spf[n] = norm * np.exp(-0.5 * omega * grid**2) * scipy.special.hermite(n)(np.sqrt(omega) * grid)
+    return spf
+
+
+def _trapz_prep(vec, dx):
+    """Trapezoid rule as a weight vector: times dx, end points halved -- one_dim_qd.py:19-27."""
+    out = vec * dx
+    out[0] *= 0.5
+    out[-1] *= 0.5
+    return out
+
+
+def odho_coulomb_elements(spf, grid, alpha, a):
+    """Two nested trapezoid integrals of ``ODHO.setup_basis`` -- ``_compute_inner_integral`` one_dim_qd.py:35-51 and
+    ``_compute_orbital_integrals`` :54-68, the same loops with the innermost dot products written as matrix
+    products: ``inner[q,s,i] = trapz_j(conj(spf_q) W(x_i, .) spf_s)``, ``u[p,q,r,s] = trapz_i(conj(spf_p) inner[q,s] spf_r)``."""
+    l, G = spf.shape
+    dx = grid[1] - grid[0]
+    inner = np.zeros((l, l, G), dtype=np.complex128)
+    for i in range(G):
+        prepped = _trapz_prep(shielded_coulomb(grid[i], grid, alpha, a), dx)
+        inner[:, :, i] = (np.conjugate(spf) * prepped) @ spf.T
+    u = np.zeros((l, l, l, l), dtype=np.complex128)
+    for q in range(l):
+        for s in range(l):
+            prepped = _trapz_prep(inner[q, s].copy(), dx)
+            u[:, q, :, s] = (np.conjugate(spf) * prepped) @ spf.T.astype(np.complex128)
+    return u
+
+
+def odho_position_elements(l, omega, dtype=np.float64):
+    """Analytic ``<n| x |n+1>`` of ``ODHO.construct_position_integrals`` -- one_dim_qd.py:150-166."""
+    position = np.zeros((1, l, l), dtype=dtype)
+    for n in range(l - 1):
+        nn = 1.0 / np.sqrt(2**n * scipy.special.factorial(n)) * (omega / np.pi) ** 0.25
+        nn_up = 1.0 / np.sqrt(2 ** (n + 1) * scipy.special.factorial(n + 1)) * (omega / np.pi) ** 0.25
+        pos = nn * nn_up * (n + 1) * np.sqrt(np.pi) * 2**n * scipy.special.factorial(n) / omega
+        position[0, n, n + 1] = pos
+        position[0, n + 1, n] = pos
+    return position
+
+
+def odho_setup_basis(l, grid_length, num_grid_points, omega=0.25, a=0.25, alpha=1.0):
+    """Everything ``ODHO.setup_basis`` stores -- one_dim_qd.py:115-134.  Returns a dict."""
+    grid = np.linspace(-grid_length, grid_length, num_grid_points)
+    eps = omega * (np.arange(l) + 0.5)
+    spf = odho_functions(l, grid, omega)
+    return {
+        "grid": grid,
+        "eigen_energies": eps,
+        "spf": spf,
+        "h": np.diag(eps).astype(np.complex128),
+        "s": np.eye(l),
+        "u": odho_coulomb_elements(spf, grid, alpha, a),
+        "position": odho_position_elements(l, omega, spf.dtype),
     }
 
 

@@ -191,3 +191,17 @@ def test_sinc_dvr_oracle_matches_reference_run():
     np.testing.assert_allclose(oracle.transform_two_body_elements(g["4d_u"], C, Ct), g["tb_biorth"], atol=1e-11)
     np.testing.assert_allclose(g["tb_dense_4d"], g["tb_biorth"], atol=1e-11)
     np.testing.assert_array_equal(oracle.sinc_dvr_add_spin_two_body(np.arange(4.0).reshape(2, 2))[:2, :2], np.zeros((2, 2)))
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_odho_reference_run(tag):
+    """Oracle restatement of the ODHO trapezoid path against a run of the unmodified reference
+    (tests/golden/make_golden_odho.py; one_dim_qd.py:35-166)."""
+    g = load_golden("odho_reference_run")
+    kw = {k[len(tag) + 5:]: g[k].item() for k in g if k.startswith(tag + "_arg_")}
+    od = oracle.odho_setup_basis(**kw)
+    for key in ("h", "s", "spf", "position", "grid", "eigen_energies"):
+        assert od[key].dtype == g[f"{tag}_{key}"].dtype, key
+        assert_close_scaled(od[key], g[f"{tag}_{key}"], rel=1e-14)
+    assert od["u"].dtype == np.complex128
+    assert_close_scaled(od["u"], g[f"{tag}_u"], rel=1e-13)
