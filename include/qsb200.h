@@ -126,6 +126,17 @@ int qs_quarter_transform_scatter(const void* A, int a_dtype, int64_t X, int64_t 
                                  int64_t x_mid, int64_t sx0, int64_t sx1, int64_t sx2,
                                  int64_t w_inner, int64_t sw0, int64_t w_deal, void* stream);
 
+/* Epilogue of the quarter GEMM.  Besides storing from registers, a launch can stage each warp's accumulator tile
+ * in shared memory ([column][row], 16 real columns at a time, two 4 KiB buffers per warp) and hand every run of rows
+ * that is contiguous in the output to the copy engine (cp.async.bulk shared -> global, SASS UBLKCP.G.S), going on
+ * to its next tile while the copies drain.  mode 0: register stores everywhere; 1 (default): staged epilogue in the
+ * scattering launches, whose stores cross NVLink; 2: wherever the alignment conditions hold (consecutive rows
+ * adjacent in the output, every run 16-byte aligned).  Measured on B200s (profiles/r02d_*, r02e_*, r02f_*): for
+ * local stores the register epilogue is 1-6 % faster; over NVLink the two are within 1 % of each other -- every
+ * store shape reaches the same 712 GB/s (profiles/r02b_peer_store_probe_2gpu.jsonl).  Returns the previous mode.
+ * Also settable with QS_BULK=off|scatter|all in the environment (read once). */
+int qs_set_bulk_epilogue_mode(int mode);
+
 /* Four-index transform of an operator that is diagonal in the original basis, u[a,b,c,d] = W[a,b] d_ac d_bd
  * (the sinc-DVR storage u_repr = "2d"):
  *   out[p,q,r,s] = sum_ab Ct[p,a] C[a,r] Ct[q,b] C[b,s] W[a,b]   ( - out[p,q,s,r] if anti_symmetrize )

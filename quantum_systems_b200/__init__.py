@@ -15,7 +15,7 @@ from .system import QuantumSystem
 from .general_orbital_system import GeneralOrbitalSystem
 from .spatial_orbital_system import SpatialOrbitalSystem
 from .random_basis import RandomBasisSet
-from .odqd import ODQD
+from .odqd import ODHO, ODQD
 from .sinc_dvr import ODSincDVR
 from . import time_evolution_operators  # noqa: F401
 from . import two_dim_ho  # noqa: F401
@@ -34,6 +34,7 @@ __all__ = [
     "SpatialOrbitalSystem",
     "RandomBasisSet",
     "ODQD",
+    "ODHO",
     "ODSincDVR",
     "TwoDimensionalHarmonicOscillator",
     "TwoDimensionalDoubleWell",

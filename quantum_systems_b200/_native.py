@@ -67,6 +67,7 @@ SIGNATURES = {
     "qs_extract_block": [_ptr, _int, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr],
     "qs_scale_add": [_ptr, _ptr, _int, _i64, _dbl, _dbl, _dbl, _dbl, _ptr, _ptr],
     "qs_occupied_traces": [_ptr, _int, _ptr, _int, _i64, _i64, _i64, _i64, _ptr, _ptr],
+    "qs_set_bulk_epilogue_mode": [_int],
     "qs_launch_count": [],
     "qs_kernel_timing_enable": [_int],
     "qs_kernel_timing_read": [_int, ctypes.POINTER(_dbl), ctypes.POINTER(_dbl), ctypes.POINTER(_i64)],

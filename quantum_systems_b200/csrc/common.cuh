@@ -80,7 +80,7 @@ int64_t qs_tile_list_bytes(int64_t X, int64_t K, int64_t W, int a_dtype, int m_d
 int qs_quarter_transform_masked(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda, const void* image,
                                 int m_dtype, int64_t W, void* out, int64_t x_inner, int64_t sx0, int64_t sx1,
                                 int64_t w_inner, int64_t sw0, int64_t sw1, const QsTileMask* mask, void* list_ws,
-                                const long long* xq_table, const long long* xr_table, void* stream);
+                                const long long* xq_table, const long long* xr_table, int xq_even, void* stream);
 
 int qs_mirror_fill(void* out, int dtype, int64_t m, int mode, void* stream);
 
@@ -156,6 +156,17 @@ __device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, dou
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(d0), "+d"(d1)
                  : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void sts_128(uint32_t addr, double a, double b) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(a), "d"(b) : "memory");
+}
+
+// Asynchronous bulk copy shared -> global (16-byte aligned on both sides, size a multiple of 16 B), tracked by the
+// issuing thread's bulk async-groups (cp.async.bulk.commit_group / wait_group[.read]).
+__device__ __forceinline__ void bulk_store(void* dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes)
+                 : "memory");
 }
 
 __device__ __forceinline__ double2 lds_128(uint32_t addr) {

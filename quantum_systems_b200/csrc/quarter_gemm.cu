@@ -66,6 +66,8 @@ struct QuarterParams {
     uint32_t x_inner, x_mid, w_inner;
     long long sx0, sx1, sx2, sw0, sw1;
     int vec2;                 // real output: row pairs (x, x + 1), x even, are adjacent and 16-byte aligned
+    int bulk;                 // staged asynchronous epilogue (BULK kernels): consecutive rows of a block are adjacent
+                              // in the output and every run starts 16-byte aligned (see launch conditions)
     // Column dealing (scattering store): logical output column j of the tile order is the physical column
     // (j * deal_mul) % deal_mod, so every CTA tile's columns are spread over ALL destinations and the NVLink
     // traffic of a launch is uniform in time (contiguous column ranges make every rank write to the same one or
@@ -99,15 +101,24 @@ __device__ __forceinline__ uint32_t dealt_column(uint32_t w, uint32_t mul, uint3
 //     column own 16 consecutive rows, so the epilogue writes whole 128-byte lines with 16-byte stores.
 __device__ __forceinline__ int row_base(int g) { return 2 * ((g >> 1) & 1) + 4 * (g & 1) + 8 * (g >> 2); }
 
-// One stage ring per MMA group: as many 16 KiB + NT KiB stages as fit, at most 6 (4 at NT = 8).
-template <int NT>
+// Staged epilogue (BULK kernels): every MMA warp owns two 4 KiB staging buffers in shared memory.
+constexpr int kStagingPerWarp = 2 * 4096;
+constexpr int kStagingBytes = kMmaWarps * kStagingPerWarp;  // 64 KiB
+
+// One stage ring per MMA group: as many 16 KiB + NT KiB stages as fit, at most 6 (4 at NT = 8; with the staging
+// buffers of the BULK epilogue 3 at NT >= 5, else 4).
+template <int NT, bool BULK = false>
 struct RingConfig {
     static constexpr int kBTileBytes = NT * 1024;  // 16 k' x 8*NT w' doubles
     static constexpr int kStageBytes = kATileBytes + kBTileBytes;
-    static constexpr int kFit = (110 * 1024) / kStageBytes;
+    static constexpr int kGroupBudget = BULK ? (227 * 1024 - kStagingBytes - 3 * 1024) / kGroups : 110 * 1024;
+    static constexpr int kFit = kGroupBudget / kStageBytes;
     static constexpr int kStages = QS_STAGES > 0 ? QS_STAGES : (kFit < 6 ? kFit : 6);
     static constexpr int kRingBytes = kStages * kStageBytes;
-    static constexpr int kSmemBytes = kGroups * kRingBytes + (kGroups * 2 * kStages + 2) * 8 + 1024;
+    static constexpr int kBarrierBytes = (kGroups * 2 * kStages + 2) * 8;
+    // rings | barriers (padded to 128 B) | staging buffers ; + 1 KiB slack for the 1 KiB alignment of the rings
+    static constexpr int kStagingOffset = kGroups * kRingBytes + (kBarrierBytes + 127) / 128 * 128;
+    static constexpr int kSmemBytes = kStagingOffset + (BULK ? kStagingBytes : 0) + 1024;
 };
 
 // One persistent CTA per SM, 12 warps:
@@ -122,10 +133,15 @@ struct RingConfig {
 // phase -- the group that is behind runs at full speed while the one ahead stores -- and nothing hides them
 // (measured 81 % of the DMMA peak); with strict alternation (one group at a time) a lone warp per sub-partition
 // cannot hide its own LDS/scoreboard stalls (measured 86 %).
-template <int NT, bool COMPLEX_OUT>
+// BULK: the epilogue does not store from registers.  Each warp drops its 32 x 8NT accumulator tile, 16 real columns
+// at a time, into a shared-memory staging buffer laid out [column][row] and hands every run of rows that is
+// contiguous in the output (256 bytes for a real, 512 bytes for a complex column) to the copy engine with
+// cp.async.bulk shared -> global.  The warp goes on to its next tile while the copies drain: the stores -- over
+// NVLink in the scattering launches -- no longer hold the tensor pipe through the depth of the store queue.
+template <int NT, bool COMPLEX_OUT, bool BULK>
 __global__ void __launch_bounds__(kThreads, 1)
 quarter_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ QuarterParams p) {
-    using Ring = RingConfig<NT>;
+    using Ring = RingConfig<NT, BULK>;
     constexpr int kBTileBytes = Ring::kBTileBytes;
     constexpr int kStageBytes = Ring::kStageBytes;
     constexpr int kStages = Ring::kStages;
@@ -229,6 +245,7 @@ quarter_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     };
 #endif
 
+    uint32_t bulk_pass = 0;  // BULK: staging passes done so far (selects the buffer, bounds the pending copy groups)
     for (uint32_t i = group; i < my_tiles; i += kGroups) {
         const uint32_t tile = p.tile_list ? p.tile_list[blockIdx.x + i * gridDim.x] : blockIdx.x + i * gridDim.x;
 
@@ -341,6 +358,90 @@ quarter_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #endif
         const uint32_t tile_w = tile % (uint32_t)p.tiles_w;
         const uint32_t x0 = (tile / (uint32_t)p.tiles_w) * kBlockX;
+        const uint32_t wbase = p.w_first + tile_w * (8 * NT);
+        const bool plain_w = p.w_inner == 1 && p.ndest == 0;  // plain rotated store: column address = w * sw1
+        if constexpr (BULK) {
+            constexpr int ES = COMPLEX_OUT ? 16 : 8;         // bytes per output element
+            constexpr int CPP = COMPLEX_OUT ? 8 : 16;        // output columns per pass (16 real accumulator columns)
+            constexpr int COL_BYTES = 32 * ES;               // one staged column: this warp's 32 rows
+            constexpr int PASSES = (NT + 1) / 2;
+            const uint32_t stage0 = smem_base + Ring::kStagingOffset + (uint32_t)warp * kStagingPerWarp;
+            // this warp's rows [xw0, xw0 + nrow) fall into blocks xq of x_inner rows; consecutive rows of a block
+            // are adjacent in the output (sx0 = 1): one run per block
+            const uint32_t xw0 = x0 + 32 * wg;
+            const uint32_t nrow = xw0 < p.X ? (p.X - xw0 < 32u ? p.X - xw0 : 32u) : 0u;
+            const uint32_t xq0 = xw0 / p.x_inner;
+            const uint32_t xr0 = xw0 - xq0 * p.x_inner;
+            const uint32_t nruns = nrow ? (xr0 + nrow + p.x_inner - 1) / p.x_inner : 0u;
+            const uint32_t items = CPP * nruns;              // (column, run) pairs per pass
+#pragma unroll
+            for (int pass = 0; pass < PASSES; ++pass) {
+                const uint32_t buf = stage0 + (uint32_t)((bulk_pass + pass) & 1) * 4096u;
+                // the copies issued from this buffer two passes ago have read it (at most one group may be pending)
+                if (bulk_pass + pass >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                __syncwarp();
+#pragma unroll
+                for (int ntl = 0; ntl < 2; ++ntl) {
+                    const int nt = 2 * pass + ntl;
+                    if (nt < NT) {
+                        if (COMPLEX_OUT) {
+                            // complex column 4 ntl + t of the pass, element (re, im) = acc[mt][nt][0..1]
+                            const uint32_t col = buf + (uint32_t)(4 * ntl + t) * COL_BYTES;
+#pragma unroll
+                            for (int mt = 0; mt < 4; ++mt)
+                                sts_128(col + (uint32_t)(rbase + (mt & 1) + 16 * (mt >> 1)) * 16u, acc[mt][nt][0],
+                                        acc[mt][nt][1]);
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const uint32_t col = buf + (uint32_t)(8 * ntl + 2 * t + e) * COL_BYTES;
+                                sts_128(col + (uint32_t)rbase * 8u, acc[0][nt][e], acc[1][nt][e]);
+                                sts_128(col + (uint32_t)(rbase + 16) * 8u, acc[2][nt][e], acc[3][nt][e]);
+                            }
+                        }
+                    }
+                }
+                // generic-proxy writes -> async-proxy reads of the copy engine
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                for (uint32_t it = lane; it < items; it += 32) {
+                    const uint32_t c = it % CPP, run = it / CPP;
+                    const uint32_t wl = (COMPLEX_OUT ? (wbase >> 1) : wbase) + (uint32_t)(CPP * pass) + c;  // output column
+                    // padding columns of the last column tile, and the absent second column group of an odd NT
+                    if (wl >= (COMPLEX_OUT ? (p.Wp >> 1) : p.Wp) || 2 * pass + (int)(c / (CPP / 2)) >= NT) continue;
+                    const uint32_t w = dealt_column(wl, p.deal_mul, p.deal_mod);
+                    double* colp;
+                    if (plain_w) {
+                        colp = p.out + (ES / 8) * ((long long)w * p.sw1);
+                    } else {
+                        const uint32_t wq = w / p.w_inner;
+                        const uint32_t wr = w - wq * p.w_inner;
+                        colp = (p.ndest ? p.outs[wq] : p.out) + (ES / 8) * ((long long)wq * p.sw1 + (long long)wr * p.sw0);
+                    }
+                    // run `run`: rows [rs, rs + len) of the warp's 32, block xq0 + run, first row of the block xr
+                    const uint32_t rs = run ? run * p.x_inner - xr0 : 0u;
+                    const uint32_t xr = run ? 0u : xr0;
+                    uint32_t len = p.x_inner - xr;
+                    if (len > nrow - rs) len = nrow - rs;
+                    const uint32_t xq = xq0 + run;
+                    long long off = xr;
+                    if (p.x_mid != 0xFFFFFFFFu) {
+                        const uint32_t x2 = xq / p.x_mid;
+                        const uint32_t x1 = xq - x2 * p.x_mid;
+                        off += (long long)x2 * p.sx2 + (long long)x1 * p.sx1;
+                    } else if (p.xq_table) {
+                        const long long tq = p.xq_table[xq];
+                        if (tq < 0) continue;  // rows the symmetry does not need
+                        off += tq;
+                    } else {
+                        off += (long long)xq * p.sx1;
+                    }
+                    bulk_store(colp + (ES / 8) * off, buf + c * COL_BYTES + rs * ES, len * ES);
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            bulk_pass += PASSES;
+        } else {
         long long xoff[4];
         bool xok[4];
 #pragma unroll
@@ -363,8 +464,6 @@ quarter_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
             xoff[mt] = off;
         }
-        const uint32_t wbase = p.w_first + tile_w * (8 * NT);
-        const bool plain_w = p.w_inner == 1 && p.ndest == 0;  // plain rotated store: column address = w * sw1
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
             const uint32_t wp = wbase + 8 * nt + 2 * t;  // real column of acc[..][nt][0]; wp + 1 for [1]
@@ -410,7 +509,10 @@ quarter_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 }
             }
         }
+        }  // register-store epilogue
     }
+    // the staging buffers must outlive the copies that read them; completion also orders the stores before the exit
+    if constexpr (BULK) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 
@@ -734,6 +836,18 @@ __global__ void build_image_kernel(ImageParams q, double* __restrict__ image) {
 // so no CTA tile carries more than 7 padding columns.  Each group is one persistent launch.
 // Development switch (QS_DISABLE_SPLIT=1): lower complex A x real M through the generic 4M image instead.
 const bool g_disable_split = getenv("QS_DISABLE_SPLIT") != nullptr;
+// Which launches use the staged asynchronous epilogue (QS_BULK = off | scatter | all; default scatter).  Measured on
+// a B200 (profiles/r02d_perf_bulk_vs_register_epilogue.jsonl): for LOCAL stores the register epilogue is 1-6 %
+// faster (one more ring stage, no lane-serialised copy issue), so only the scattering launches -- whose stores
+// cross NVLink and otherwise hold the warp through the depth of the store queue -- stage their tiles.
+int g_bulk_mode = -1;
+int bulk_mode() {
+    if (g_bulk_mode < 0) {
+        const char* v = getenv("QS_BULK");
+        g_bulk_mode = !v ? 1 : !strcmp(v, "off") ? 0 : !strcmp(v, "all") ? 2 : 1;
+    }
+    return g_bulk_mode;
+}
 
 struct TileGroup {
     int NT, tiles_w, w_first;
@@ -791,34 +905,35 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-template <int NT, bool CO>
+template <int NT, bool CO, bool BULK>
 int launch_variant(const CUtensorMap& map, const QuarterParams& p, cudaStream_t st) {
-    constexpr int smem = RingConfig<NT>::kSmemBytes;
+    constexpr int smem = RingConfig<NT, BULK>::kSmemBytes;
+    static_assert(smem <= 227 * 1024, "shared memory budget of one CTA per SM");
     static bool configured[kMaxDevices] = {false};  // the attribute belongs to the device's context
     const int dev = qs_current_device();
     if (!configured[dev]) {
-        QS_CUDA(cudaFuncSetAttribute(quarter_gemm_kernel<NT, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        QS_CUDA(cudaFuncSetAttribute(quarter_gemm_kernel<NT, CO, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured[dev] = true;
     }
     const int64_t total = p.tile_list ? (int64_t)p.n_listed : (int64_t)p.tiles_x * p.tiles_w;
     const int64_t resident = qs_sm_count();  // one persistent CTA per SM
     const int64_t grid = total < resident ? total : resident;
-    quarter_gemm_kernel<NT, CO><<<(unsigned)grid, kThreads, smem, st>>>(map, p);
+    quarter_gemm_kernel<NT, CO, BULK><<<(unsigned)grid, kThreads, smem, st>>>(map, p);
     QS_LAUNCH_CHECK();
     return QS_OK;
 }
 
-template <bool CO>
+template <bool CO, bool BULK>
 int launch_nt(int NT, const CUtensorMap& map, const QuarterParams& p, cudaStream_t st) {
     switch (NT) {
-        case 1: return launch_variant<1, CO>(map, p, st);
-        case 2: return launch_variant<2, CO>(map, p, st);
-        case 3: return launch_variant<3, CO>(map, p, st);
-        case 4: return launch_variant<4, CO>(map, p, st);
-        case 5: return launch_variant<5, CO>(map, p, st);
-        case 6: return launch_variant<6, CO>(map, p, st);
-        case 7: return launch_variant<7, CO>(map, p, st);
-        case 8: return launch_variant<8, CO>(map, p, st);
+        case 1: return launch_variant<1, CO, BULK>(map, p, st);
+        case 2: return launch_variant<2, CO, BULK>(map, p, st);
+        case 3: return launch_variant<3, CO, BULK>(map, p, st);
+        case 4: return launch_variant<4, CO, BULK>(map, p, st);
+        case 5: return launch_variant<5, CO, BULK>(map, p, st);
+        case 6: return launch_variant<6, CO, BULK>(map, p, st);
+        case 7: return launch_variant<7, CO, BULK>(map, p, st);
+        case 8: return launch_variant<8, CO, BULK>(map, p, st);
     }
     qs_set_error("internal: NT=%d out of range", NT);
     return QS_ERR_INVALID;
@@ -879,6 +994,15 @@ int build_image(ImageParams q, const Tiling& tl, void* image, void* stream) {
 }
 
 }  // namespace
+
+// 0: register stores everywhere; 1: staged asynchronous epilogue in the scattering launches (default); 2: wherever
+// the alignment conditions hold.  Returns the previous mode.  Development / test switch (also QS_BULK in the
+// environment, read once).
+extern "C" int qs_set_bulk_epilogue_mode(int mode) {
+    const int previous = bulk_mode();
+    if (mode >= 0 && mode <= 2) g_bulk_mode = mode;
+    return previous;
+}
 
 extern "C" int qs_coeff_image_bytes(int64_t K, int64_t W, int a_dtype, int m_dtype, int64_t* bytes) {
     QS_REQUIRE(K > 0 && W > 0 && bytes, "qs_coeff_image_bytes: bad arguments");
@@ -1092,7 +1216,7 @@ int quarter_launch(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda
                    int64_t sx0, int64_t sx1, int64_t sx2, int64_t w_inner, int64_t sw0, int64_t sw1, int64_t w_deal,
                    void* stream, const QsTileMask* mask = nullptr, void* list_ws = nullptr,
                    const long long* xq_table = nullptr, const long long* xr_table = nullptr,
-                   const long long* host_xq_table = nullptr) {
+                   const long long* host_xq_table = nullptr, int xq_even = 0) {
     QS_REQUIRE(A && image && (out || out_table), "qs_quarter_transform: null pointer");
     QS_REQUIRE(w_deal >= 1 && w_deal < (W > 1 ? W : 2) && gcd64(w_deal, W) == 1,
                "qs_quarter_transform_scatter: the dealing multiplier %lld is not coprime to W = %lld",
@@ -1141,6 +1265,21 @@ int quarter_launch(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda
                sw0 % 2 == 0 && (n_dest > 0 || sw1 % 2 == 0) && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
     for (int64_t d = 0; d < n_dest; ++d) vec2 = vec2 && (reinterpret_cast<uintptr_t>(out_table[d]) & 15) == 0;
     if (xq_table || xr_table) vec2 = 0;  // tabulated row offsets: adjacent rows need not be adjacent in memory
+    // Staged asynchronous epilogue: consecutive rows of a block are adjacent in the output (sx0 = 1) and every run of
+    // rows handed to cp.async.bulk starts 16-byte aligned: always for complex output (16-byte elements); for real
+    // output when all extents, strides and bases are even (the conditions of vec2), with an even row table.
+    // Rows placed one by one (xr_table) keep the register stores.
+    if (host_xq_table) {  // the caller's own table: every kept entry must be even for 16-byte aligned real runs
+        xq_even = 1;
+        for (int64_t q = 0, nq = qs_ceil_div(X, x_inner); q < nq && xq_even; ++q)
+            xq_even = host_xq_table[q] < 0 || host_xq_table[q] % 2 == 0;
+    }
+    int bulk = (bulk_mode() == 2 || (bulk_mode() == 1 && n_dest > 0)) && sx0 == 1 && !xr_table && !tl.split;
+    if (bulk && !out_complex) {
+        bulk = x_inner % 2 == 0 && X % 2 == 0 && sx1 % 2 == 0 && sx2 % 2 == 0 && sw0 % 2 == 0 &&
+               (n_dest > 0 || sw1 % 2 == 0) && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (!xq_table || xq_even);
+        for (int64_t d = 0; d < n_dest; ++d) bulk = bulk && (reinterpret_cast<uintptr_t>(out_table[d]) & 15) == 0;
+    }
 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // symmetry mask: per tile group, the ascending list of wanted linear tile ids, staged into list_ws
@@ -1205,9 +1344,10 @@ int quarter_launch(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda
         p.xq_table = xq_table;
         p.xr_table = xr_table;
         QS_REQUIRE((int64_t)p.tiles_x * p.tiles_w < (1LL << 31), "qs_quarter_transform: too many tiles");
+        p.bulk = bulk;
         const int rc = tl.split      ? launch_split(gr.NT, map, p, st)
-                       : out_complex ? launch_nt<true>(gr.NT, map, p, st)
-                                     : launch_nt<false>(gr.NT, map, p, st);
+                       : out_complex ? (bulk ? launch_nt<true, true>(gr.NT, map, p, st) : launch_nt<true, false>(gr.NT, map, p, st))
+                                     : (bulk ? launch_nt<false, true>(gr.NT, map, p, st) : launch_nt<false, false>(gr.NT, map, p, st));
         if (rc) return rc;
     }
     qs_timing_end(span, stream);
@@ -1228,9 +1368,9 @@ int64_t qs_tile_list_bytes(int64_t X, int64_t K, int64_t W, int a_dtype, int m_d
 int qs_quarter_transform_masked(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda, const void* image,
                                 int m_dtype, int64_t W, void* out, int64_t x_inner, int64_t sx0, int64_t sx1,
                                 int64_t w_inner, int64_t sw0, int64_t sw1, const QsTileMask* mask, void* list_ws,
-                                const long long* xq_table, const long long* xr_table, void* stream) {
+                                const long long* xq_table, const long long* xr_table, int xq_even, void* stream) {
     return quarter_launch(A, a_dtype, X, K, lda, image, m_dtype, W, out, nullptr, 0, x_inner, 0xFFFFFFFFLL, sx0, sx1, 0,
-                          w_inner, sw0, sw1, 1, stream, mask, list_ws, xq_table, xr_table);
+                          w_inner, sw0, sw1, 1, stream, mask, list_ws, xq_table, xr_table, nullptr, xq_even);
 }
 
 // Host-only: the tiles a masked quarter transform would launch, as rows of (first row, last row, first output

@@ -91,7 +91,7 @@ int masked_rotated_quarter(const void* A, int a_dtype, int64_t X, int64_t K, int
                            const QsTileMask* mask, void* list_ws, void* stream) {
     const int64_t plane = X / lo_extent * lo_pitch;
     return qs_quarter_transform_masked(A, a_dtype, X, K, lda, image, m_dtype, W, out, lo_extent, 1, lo_pitch, 1, 0,
-                                       plane, mask, list_ws, nullptr, nullptr, stream);
+                                       plane, mask, list_ws, nullptr, nullptr, 0, stream);
 }
 
 }  // namespace
@@ -207,11 +207,11 @@ extern "C" int qs_transform_two_body_symmetric(const void* u, int u_dtype, const
     // step 3: rows (r, s, a) -- tiles wanted iff they hold some r < s;  packed store T3p[q, pair(r, s), a]
     const QsTileMask m3 = {2, strict, M * N, M, N, M};
     if ((rc = qs_quarter_transform_masked(bufB, td, M * M * N, N, P, img3, c_dtype, M, bufA, N, 1, 0, 1, 0, npairs * P,
-                                          &m3, lists, dev_slot_of_rs, nullptr, stream)))
+                                          &m3, lists, dev_slot_of_rs, nullptr, /*xq_even=*/P % 2 == 0, stream)))
         return rc;
     // step 4: dense over rows (q, pair);  out[p, q, r, s] at p M^3 + q M^2 + (r M + s)(pair)
     if ((rc = qs_quarter_transform_masked(bufA, td, M * npairs, N, P, img3, c_dtype, M, out, npairs, 0, M * M, 1, 0,
-                                          M * M * M, nullptr, nullptr, nullptr, dev_rs_of_pair, stream)))
+                                          M * M * M, nullptr, nullptr, nullptr, dev_rs_of_pair, 0, stream)))
         return rc;
     return qs_mirror_fill(out, td, M, symmetry, stream);
 }

@@ -8,6 +8,9 @@ FP64 tensor-core GEMMs (``ops.odqd_coulomb``) instead of ``np.einsum``.
 
 import numpy as _numpy
 import scipy.linalg
+import scipy.special
+
+import torch
 
 from . import _arrays, ops, potentials
 from .basis_set import BasisSet
@@ -90,4 +93,70 @@ class ODQD(BasisSet):
 
         position = _numpy.zeros((1, self.l, self.l), dtype=_numpy.complex128)
         position[0] = (C.T * (inner + self.beta * inner**2)) @ C  # <a| x + beta x^2 |b>, O(G l^2) host
+        self.position = position
+
+
+class ODHO(BasisSet):
+    """Harmonic-oscillator eigenfunctions on a grid with trapezoid-rule Coulomb integrals (mirror of reference
+    quantum_dots/one_dim/one_dim_qd.py:71-166; not exported by the reference package either).
+
+    ``u[p,q,r,s] = trapz_i( spf_p spf_r(x_i) trapz_j( spf_q spf_s(x_j) W(x_i, x_j) ) )`` -- the reference's two numba
+    loop nests (``_compute_inner_integral`` :35-51, ``_compute_orbital_integrals`` :54-68).  With the trapezoid
+    weights ``w`` (dx, end points halved, :19-27) folded into the orbital rows, ``L[i, p] = sqrt(w_i) spf_p(x_i)``,
+    this is exactly the two-GEMM grid build of ``ODQD`` on the FULL grid,
+    ``u_abcd = sum_ij L_ia L_ic W_ij L_jb L_jd`` (``ops.odqd_coulomb``): the inner integral is never stored.
+
+    >>> # odho = ODHO(20, 11, 201, omega=1); odho.l == 20; abs(0.5 - odho.h[0, 0]) == 0
+    """
+
+    def __init__(self, l, grid_length, num_grid_points, omega=0.25, a=0.25, alpha=1.0, beta=0, **kwargs):
+        super().__init__(l, dim=1, **kwargs)
+        self.omega = omega
+        self.a = a
+        self.alpha = alpha
+        self.grid_length = grid_length
+        self.num_grid_points = num_grid_points
+        self.grid = _numpy.linspace(-self.grid_length, self.grid_length, self.num_grid_points)
+        self.beta = beta
+        self.setup_basis()
+
+    def setup_basis(self):
+        """Fill ``h, s, spf, u, position`` (one_dim_qd.py:115-134)."""
+        dx = self.grid[1] - self.grid[0]
+        self.eigen_energies = self.omega * (_numpy.arange(self.l) + 0.5)
+        self.h = _numpy.diag(self.eigen_energies).astype(_numpy.complex128)
+        self.s = _numpy.eye(self.l)
+        spf = _numpy.stack([self.ho_function(self.grid, p) for p in range(self.l)])
+        self.spf = spf
+
+        weights = _numpy.full(self.num_grid_points, dx)
+        weights[0] *= 0.5
+        weights[-1] *= 0.5
+        L = _numpy.ascontiguousarray((spf * _numpy.sqrt(weights)).T)  # (G, l): trapezoid weights in the rows
+        u = ops.odqd_coulomb(_arrays.to_device(L), _arrays.to_device(self.grid), self.alpha, self.a)
+        self.u = _arrays.to_module(u.to(torch.complex128), self.np)  # the reference allocates u as complex128
+
+        self.construct_position_integrals()
+
+    def ho_function(self, x, n):
+        """``N_n exp(-omega x^2 / 2) H_n(sqrt(omega) x)`` (one_dim_qd.py:136-141)."""
+        return (
+            self.normalization(n)
+            * _numpy.exp(-0.5 * self.omega * x**2)
+            * scipy.special.eval_hermite(n, _numpy.sqrt(self.omega) * x)
+        )
+
+    def normalization(self, n):
+        """``(omega / pi)^(1/4) / sqrt(2^n n!)`` (one_dim_qd.py:143-148)."""
+        return 1.0 / _numpy.sqrt(2.0**n * scipy.special.factorial(n)) * (self.omega / _numpy.pi) ** 0.25
+
+    def construct_position_integrals(self):
+        """Analytic ``<n| x |n+1> = N_n N_{n+1} (n+1) sqrt(pi) 2^n n! / omega`` (one_dim_qd.py:150-166)."""
+        position = _numpy.zeros((1, self.l, self.l))
+        for n in range(self.l - 1):
+            pos = (
+                self.normalization(n) * self.normalization(n + 1) * (n + 1) * _numpy.sqrt(_numpy.pi) * 2.0**n
+                * scipy.special.factorial(n) / self.omega
+            )
+            position[0, n, n + 1] = position[0, n + 1, n] = pos
         self.position = position

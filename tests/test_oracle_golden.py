@@ -5,7 +5,7 @@ unmodified reference (tests/golden/make_golden.py) and against the reference's o
 import numpy as np
 import pytest
 
-from conftest import load_golden
+from conftest import assert_close_scaled, load_golden
 from oracle import qs_oracle as oracle
 
 

@@ -24,6 +24,14 @@ def main():
     w.prepare(C, None)
     recv = ctx.shared_cached("recv", [w.recv_numel(r) for r in range(world)], torch.float64)
     out = u.spare
+    # experiment (timing only, the result is then wrong): let rank r write into block position (r + k) % W of every
+    # destination instead of position r -- does the rank-dependent scatter time follow the POSITION written?
+    k = int(os.environ.get("QS_ROTATE_POSITION", "0"))
+    if k:
+        w.a_off = list(w.a_off)
+        w.r_off = list(w.r_off)
+        w.a_off[rank] = ((rank + k) % world) * w.a_block
+        w.r_off[rank] = ((rank + k) % world) * w.r_block
     names = ["step1", "step2_scatter", "barrier", "step3", "step4_scatter", "barrier2"]
     acc = {k: [] for k in names}
     for it in range(4):
