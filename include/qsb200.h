@@ -115,7 +115,15 @@ int qs_quarter_transform(const void* A, int a_dtype, int64_t X, int64_t K, int64
  * peers at any moment (an NVLink ingress hot spot: +29 % on 7 of 8 ranks at n = 400).  `w_deal` > 1
  * (from qs_scatter_deal(W)) makes the j-th column of the tile order the PHYSICAL column (j * w_deal) % W,
  * spreading every tile over all destinations; the image must then come from qs_build_coeff_image_dealt
- * with the same multiplier.  w_deal = 1: columns in natural order (plain qs_build_coeff_image). */
+ * with the same multiplier.  w_deal = 1: columns in natural order (plain qs_build_coeff_image).
+ *
+ * Cyclic destinations.  `w_cyclic` != 0 replaces the blocks of w_inner columns per destination by a round-robin:
+ * column w goes to host_out_table[w % n_dest] and is column w / n_dest there (w_inner is then ignored).  A tile's
+ * columns spread over all destinations by themselves (no dealing needed), and the owner of the cyclic columns later
+ * writes rows that INTERLEAVE with the other ranks' rows.  That matters: eight ranks that each fill one of eight
+ * ADJACENT chunks of a block in a destination's memory at the same time see position-dependent NVLink throughput
+ * (the ranks writing the outermost chunks are 30 % slower at n = 192 on 8 B200s -- the slow ranks follow the chunk
+ * position, not the physical GPU; profiles/r02h_*, r02i_*). */
 int qs_scatter_deal(int64_t W, int64_t* w_deal);
 int qs_build_coeff_image_dealt(const void* m, int m_dtype, int64_t m_sk, int64_t m_sw, int m_conj,
                                int64_t K, int64_t W, int a_dtype, int64_t w_deal, void* image,
@@ -124,7 +132,7 @@ int qs_quarter_transform_scatter(const void* A, int a_dtype, int64_t X, int64_t 
                                  const void* image, int m_dtype, int64_t W,
                                  void* const* host_out_table, int64_t n_dest, int64_t x_inner,
                                  int64_t x_mid, int64_t sx0, int64_t sx1, int64_t sx2,
-                                 int64_t w_inner, int64_t sw0, int64_t w_deal, void* stream);
+                                 int64_t w_inner, int64_t sw0, int64_t w_deal, int w_cyclic, void* stream);
 
 /* Epilogue of the quarter GEMM.  Besides storing from registers, a launch can stage each warp's accumulator tile
  * in shared memory ([column][row], 16 real columns at a time, two 4 KiB buffers per warp) and hand every run of rows

@@ -73,6 +73,11 @@ struct QuarterParams {
     // traffic of a launch is uniform in time (contiguous column ranges make every rank write to the same one or
     // two peers at once: measured +29 % on 7 of 8 ranks at n = 400).  deal_mul == 1: identity.
     uint32_t deal_mul, deal_mod;
+    // Cyclic destinations (scattering store): column w belongs to destination w % ndest and is column w / ndest there
+    // (instead of blocks of w_inner columns per destination).  Consecutive columns then go to different
+    // destinations by themselves, and a rank that owns the cyclic columns writes rows INTERLEAVED with the other
+    // ranks' rows later on, never one of W adjacent chunks of a block (see sharded.py, "where the tiles land").
+    int w_cyclic;
     // Optional tile list (symmetry-aware transforms): when non-null the launch visits only the n_listed linear
     // tile ids (row_tile * tiles_w + col_tile, ascending) stored there instead of all tiles_x * tiles_w tiles.
     const uint32_t* tile_list;
@@ -414,8 +419,8 @@ quarter_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     if (plain_w) {
                         colp = p.out + (ES / 8) * ((long long)w * p.sw1);
                     } else {
-                        const uint32_t wq = w / p.w_inner;
-                        const uint32_t wr = w - wq * p.w_inner;
+                        const uint32_t wq = p.w_cyclic ? w % (uint32_t)p.ndest : w / p.w_inner;
+                        const uint32_t wr = p.w_cyclic ? w / (uint32_t)p.ndest : w - wq * p.w_inner;
                         colp = (p.ndest ? p.outs[wq] : p.out) + (ES / 8) * ((long long)wq * p.sw1 + (long long)wr * p.sw0);
                     }
                     // run `run`: rows [rs, rs + len) of the warp's 32, block xq0 + run, first row of the block xr
@@ -474,8 +479,8 @@ quarter_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     if (plain_w) {
                         col = p.out + 2 * ((long long)w * p.sw1);
                     } else {
-                        const uint32_t wq = w / p.w_inner;
-                        const uint32_t wr = w - wq * p.w_inner;
+                        const uint32_t wq = p.w_cyclic ? w % (uint32_t)p.ndest : w / p.w_inner;
+                        const uint32_t wr = p.w_cyclic ? w / (uint32_t)p.ndest : w - wq * p.w_inner;
                         col = (p.ndest ? p.outs[wq] : p.out) + 2 * ((long long)wq * p.sw1 + (long long)wr * p.sw0);
                     }
 #pragma unroll
@@ -492,8 +497,8 @@ quarter_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         if (plain_w) {
                             col = p.out + (long long)w * p.sw1;
                         } else {
-                            const uint32_t wq = w / p.w_inner;
-                            const uint32_t wr = w - wq * p.w_inner;
+                            const uint32_t wq = p.w_cyclic ? w % (uint32_t)p.ndest : w / p.w_inner;
+                            const uint32_t wr = p.w_cyclic ? w / (uint32_t)p.ndest : w - wq * p.w_inner;
                             col = (p.ndest ? p.outs[wq] : p.out) + (long long)wq * p.sw1 + (long long)wr * p.sw0;
                         }
                         if (p.vec2) {
@@ -728,8 +733,8 @@ quarter_gemm_split_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                 if (plain_w) {
                     col = p.out + 2 * ((long long)w * p.sw1);
                 } else {
-                    const uint32_t wq = w / p.w_inner;
-                    const uint32_t wr = w - wq * p.w_inner;
+                    const uint32_t wq = p.w_cyclic ? w % (uint32_t)p.ndest : w / p.w_inner;
+                    const uint32_t wr = p.w_cyclic ? w / (uint32_t)p.ndest : w - wq * p.w_inner;
                     col = (p.ndest ? p.outs[wq] : p.out) + 2 * ((long long)wq * p.sw1 + (long long)wr * p.sw0);
                 }
 #pragma unroll
@@ -1216,7 +1221,7 @@ int quarter_launch(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda
                    int64_t sx0, int64_t sx1, int64_t sx2, int64_t w_inner, int64_t sw0, int64_t sw1, int64_t w_deal,
                    void* stream, const QsTileMask* mask = nullptr, void* list_ws = nullptr,
                    const long long* xq_table = nullptr, const long long* xr_table = nullptr,
-                   const long long* host_xq_table = nullptr, int xq_even = 0) {
+                   const long long* host_xq_table = nullptr, int xq_even = 0, int w_cyclic = 0) {
     QS_REQUIRE(A && image && (out || out_table), "qs_quarter_transform: null pointer");
     QS_REQUIRE(w_deal >= 1 && w_deal < (W > 1 ? W : 2) && gcd64(w_deal, W) == 1,
                "qs_quarter_transform_scatter: the dealing multiplier %lld is not coprime to W = %lld",
@@ -1227,9 +1232,10 @@ int quarter_launch(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda
                    x_mid < (1LL << 32),
                "qs_quarter_transform: bad inner extents");
     QS_REQUIRE(n_dest >= 0 && n_dest <= kMaxDest, "qs_quarter_transform_scatter: at most %d destinations", kMaxDest);
-    QS_REQUIRE(n_dest == 0 || qs_ceil_div(W, w_inner) <= n_dest,
+    QS_REQUIRE(n_dest == 0 || w_cyclic || qs_ceil_div(W, w_inner) <= n_dest,
                "qs_quarter_transform_scatter: W=%lld needs more than %lld destinations of %lld", (long long)W,
                (long long)n_dest, (long long)w_inner);
+    QS_REQUIRE(!w_cyclic || n_dest > 0, "qs_quarter_transform_scatter: cyclic columns need a destination table");
     const Tiling tl = make_tiling(K, W, a_dtype, m_dtype);
     const bool out_complex = a_dtype == QS_C128 || m_dtype == QS_C128;
     const int64_t pitch_bytes = lda * 8 * qs_elem_doubles(a_dtype);
@@ -1274,7 +1280,7 @@ int quarter_launch(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda
         for (int64_t q = 0, nq = qs_ceil_div(X, x_inner); q < nq && xq_even; ++q)
             xq_even = host_xq_table[q] < 0 || host_xq_table[q] % 2 == 0;
     }
-    int bulk = (bulk_mode() == 2 || (bulk_mode() == 1 && n_dest > 0)) && sx0 == 1 && !xr_table && !tl.split;
+    int bulk = (bulk_mode() == 2 || (bulk_mode() == 1 && n_dest > 1)) && sx0 == 1 && !xr_table && !tl.split;
     if (bulk && !out_complex) {
         bulk = x_inner % 2 == 0 && X % 2 == 0 && sx1 % 2 == 0 && sx2 % 2 == 0 && sw0 % 2 == 0 &&
                (n_dest > 0 || sw1 % 2 == 0) && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (!xq_table || xq_even);
@@ -1341,6 +1347,7 @@ int quarter_launch(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda
         p.vec2 = vec2;
         p.deal_mul = (uint32_t)w_deal;
         p.deal_mod = (uint32_t)W;
+        p.w_cyclic = w_cyclic;
         p.xq_table = xq_table;
         p.xr_table = xr_table;
         QS_REQUIRE((int64_t)p.tiles_x * p.tiles_w < (1LL << 31), "qs_quarter_transform: too many tiles");
@@ -1451,8 +1458,9 @@ extern "C" int qs_quarter_transform_scatter(const void* A, int a_dtype, int64_t 
                                             const void* image, int m_dtype, int64_t W, void* const* host_out_table,
                                             int64_t n_dest, int64_t x_inner, int64_t x_mid, int64_t sx0, int64_t sx1,
                                             int64_t sx2, int64_t w_inner, int64_t sw0, int64_t w_deal,
-                                            void* stream) {
+                                            int w_cyclic, void* stream) {
     QS_REQUIRE(host_out_table && n_dest > 0, "qs_quarter_transform_scatter: empty destination table");
     return quarter_launch(A, a_dtype, X, K, lda, image, m_dtype, W, nullptr, host_out_table, n_dest, x_inner, x_mid, sx0,
-                          sx1, sx2, w_inner, sw0, 0, w_deal, stream);
+                          sx1, sx2, w_inner, sw0, 0, w_deal, stream, nullptr, nullptr, nullptr, nullptr, nullptr, 0,
+                          w_cyclic);
 }

@@ -216,14 +216,14 @@ class CudaEngine:
         return out
 
     def quarter_scatter(self, A, X, K, lda, image, m_dtype, W, dests, x_inner, x_mid, sx0, sx1, sx2, w_inner, sw0,
-                        deal=1):
+                        deal=1, cyclic=False):
         if X <= 0:
             return
         table = (ctypes.c_void_p * len(dests))(*[buf.at(off) for buf, off in dests])
         _native.call(
             "qs_quarter_transform_scatter", ctypes.c_void_p(A.at(0)), _CODES[A.dtype], X, K, lda,
             ctypes.c_void_p(image.data_ptr()), _CODES[m_dtype], W, table, len(dests), x_inner, max(x_mid, 1), sx0, sx1,
-            sx2, w_inner, sw0, int(deal), self._stream(),
+            sx2, max(w_inner, 1), sw0, int(deal), int(bool(cyclic)), self._stream(),
         )
 
 
@@ -553,21 +553,57 @@ class ShardedTwoBody:
 # one rank's share of a sharded four-index transform
 # ------------------------------------------------------------------------------------------------
 class _RankTransform:
+    """One rank's share of a sharded four-index transform.
+
+    Where the tiles land (peer schedule).  Eight ranks that each fill ONE OF EIGHT ADJACENT CHUNKS of a block in a
+    destination's memory at the same time get position-dependent NVLink throughput: at n = 192 on 8 B200s the ranks
+    writing the outermost chunks needed 2.9 ms for a scattering step, the middle ones 2.2 ms, and the slow ranks
+    followed the chunk position when it was rotated, not the physical GPU (profiles/r02g_*, r02h_*).  With streams
+    that are far apart or interleaved row by row every rank needs 2.04 ms (profiles/r02i_*).  Hence
+
+    * the intermediate index r is dealt to the ranks CYCLICALLY (rank j owns r = j, j + W, ...): in the final
+      store u'[p_loc, q, r, s] a rank's rows interleave with the other ranks' rows inside every (r, s) block, and
+      in the first exchange consecutive columns go to different destinations by themselves;
+    * the received half-transformed tensor is kept SOURCE-MAJOR, ``T2[src][r_loc][s][a_loc][b]``: each source
+      writes one contiguous region of the destination instead of a chunk of every (a, b) block.
+
+    Both are internal: the input stays block-partitioned on its leading index a, the result on p.  The collective
+    schedule (validation path) keeps the block partition of r.
+    """
+
     def __init__(self, ctx, rank, n, m, u_dtype, c_dtype):
         self.ctx, self.rank, self.n, self.m = ctx, rank, n, m
         self.engine = ctx.engine
         self.u_dtype, self.c_dtype = u_dtype, c_dtype
         self.t_dtype = torch.complex128 if torch.complex128 in (u_dtype, c_dtype) else torch.float64
         self.a_block, self.a_off = block_partition(n, ctx.world)  # partition of the old leading index
-        self.r_block, self.r_off = block_partition(m, ctx.world)  # partition of the new indices r and p
+        self.r_block, self.r_off = block_partition(m, ctx.world)  # partition of the new leading index p (and of r
+        #                                                           in the collective schedule)
+        self.cyclic = ctx.exchange == "peer"                       # peer schedule: r is dealt cyclically
         self.Pu = padded_pitch(n, u_dtype)
         self.P = padded_pitch(n, self.t_dtype)
         self.A = self.a_off[rank + 1] - self.a_off[rank]
-        self.R = self.r_off[rank + 1] - self.r_off[rank]
+        self.R = self.r_count(rank)
+        # every source holds the same number of planes: step 3 reads the source-major T2 in one launch
+        self.even_sources = all(self.a_off[j + 1] - self.a_off[j] == self.A for j in range(ctx.world))
+
+    def r_count(self, rank):
+        """Number of intermediate indices r that `rank` owns."""
+        if self.cyclic:
+            return len(range(rank, self.m, self.ctx.world))
+        return self.r_off[rank + 1] - self.r_off[rank]
+
+    def r_values(self):
+        """The intermediate indices r of this rank, in the order of its local index r_loc."""
+        import numpy
+
+        if self.cyclic:
+            return numpy.arange(self.rank, self.m, self.ctx.world, dtype=numpy.int64)
+        return self.r_off[self.rank] + numpy.arange(self.R, dtype=numpy.int64)
 
     # sizes (elements of t_dtype unless noted)
     def recv_numel(self, rank):
-        return (self.r_off[rank + 1] - self.r_off[rank]) * self.m * self.n * self.P
+        return self.r_count(rank) * self.m * self.n * self.P
 
     def out_numel(self, rank):
         return (self.r_off[rank + 1] - self.r_off[rank]) * self.m**3
@@ -583,17 +619,17 @@ class _RankTransform:
             self.img3 = eng.image(C_tilde, n, m, self.t_dtype, 1, n)
         else:
             self.img3 = eng.image(C, n, m, self.t_dtype, m, 1, conj=True)  # C~ = C^dagger, basis_set.py:338-339
-        # The scattering steps deal their output columns over all destinations (uniform NVLink traffic): their
-        # images hold the columns of C / C~ in dealt order.
+        # The last step scatters BLOCKS of the new leading index p (the result is block-partitioned), so it deals
+        # its output columns over all destinations (uniform NVLink traffic): its image holds the columns of C~ in
+        # dealt order.  The first exchange sends cyclic columns and needs no dealing.
         self.deal = eng.scatter_deal(m) if self.ctx.exchange == "peer" and self.ctx.world > 1 else 1
         if self.deal > 1:
-            self.img2_scatter = eng.image(C, n, m, self.t_dtype, m, 1, deal=self.deal)
             if C_tilde is not None:
                 self.img4_scatter = eng.image(C_tilde, n, m, self.t_dtype, 1, n, deal=self.deal)
             else:
                 self.img4_scatter = eng.image(C, n, m, self.t_dtype, m, 1, conj=True, deal=self.deal)
         else:
-            self.img2_scatter, self.img4_scatter = self.img2, self.img3
+            self.img4_scatter = self.img3
         self.scratch = eng.empty(self.scratch_numel(), self.t_dtype)
 
     def step1(self, u_in):
@@ -609,13 +645,15 @@ class _RankTransform:
         eng.quarter(src, A * n * n, n, self.Pu, self.img1, self.c_dtype, m, self.scratch, 0, n, 1, P, 1, 0, A * n * P)
 
     def step2_scatter(self, recv):
-        """T2[r, s, a, b] = sum_c T1[s, a_loc, b, c] C[c, r], stored into the rank that owns r at
-        [r_loc][s][a][b] (b at pitch P): the a -> r re-partition rides on the epilogue."""
+        """T2[r, s, a, b] = sum_c T1[s, a_loc, b, c] C[c, r], stored into the rank that owns r (cyclic: r % W) at
+        [src = this rank][r_loc = r // W][s][a_loc][b] (b at pitch P): the a -> r re-partition rides on the epilogue,
+        and this rank's tiles fill ONE contiguous region of every destination."""
         eng, n, m, A, P = self.engine, self.n, self.m, self.A, self.P
         a0 = self.a_off[self.rank]
-        dests = [(recv[j], a0 * P) for j in range(self.ctx.world)]
-        eng.quarter_scatter(self.scratch, m * A * n, n, P, self.img2_scatter, self.c_dtype, m, dests, n, A, 1, P, n * P,
-                            self.r_block, m * n * P, deal=self.deal)
+        # region of this source in destination j: behind the regions of the sources before it
+        dests = [(recv[j], a0 * self.r_count(j) * m * P) for j in range(self.ctx.world)]
+        eng.quarter_scatter(self.scratch, m * A * n, n, P, self.img2, self.c_dtype, m, dests, n, A, 1, P, A * P,
+                            0, m * A * P, deal=1, cyclic=True)
 
     def step2_local(self, send):
         """Collective schedule: T2[r, s, a_loc, b] written locally, blocks of r contiguous per destination."""
@@ -623,13 +661,21 @@ class _RankTransform:
         eng.quarter(self.scratch, m * A * n, n, P, self.img2, self.c_dtype, m, send, 0, n, 1, P, 1, 0, m * A * P)
 
     def step3(self, recv_local):
-        """T3[q, r_loc, s, a] = sum_b T2[r_loc, s, a, b] C~[q, b]."""
+        """T3[q, r_loc, s, a] = sum_b T2[src][r_loc][s][a_loc][b] C~[q, b]: the rows arrive source-major and are
+        stored with a = a_off[src] + a_loc.  One launch when every source holds the same number of planes (three-level
+        row split through the single-destination form of the scattering store), else one launch per source."""
         eng, n, m, R, P = self.engine, self.n, self.m, self.R, self.P
-        eng.quarter(recv_local, R * m * n, n, P, self.img3, self.c_dtype, m, self.scratch, 0, n, 1, P, 1, 0, R * m * P)
+        if R == 0:
+            return
+        if self.even_sources:
+            eng.quarter_scatter(recv_local, R * m * n, n, P, self.img3, self.c_dtype, m, [(self.scratch, 0)], self.A,
+                                R * m, 1, P, self.A, m, R * m * P, deal=1)
+        else:
+            self.step3_blocked(recv_local)
 
     def step3_blocked(self, recv_blocks):
-        """Collective schedule: the received buffer is [src][r_loc][s][a_loc(src)][b]; one launch per source
-        drops its planes between the others' (a at pitch P in T3)."""
+        """The received buffer is [src][r_loc][s][a_loc(src)][b]; one launch per source drops its planes between the
+        others' (a at pitch P in T3).  Also the collective schedule's step 3."""
         eng, n, m, R, P = self.engine, self.n, self.m, self.R, self.P
         offset = 0
         for src in range(self.ctx.world):
@@ -643,46 +689,62 @@ class _RankTransform:
 
     def step4_scatter(self, out):
         """u'[p, q, r, s] = sum_a T3[q, r_loc, s, a] C~[p, a], stored into the rank that owns p at
-        [p_loc][q][r][s]: the result is sharded on its leading index again."""
-        eng, n, m, R, P = self.engine, self.n, self.m, self.R, self.P
-        r0 = self.r_off[self.rank]
-        dests = [(out[j], r0 * m) for j in range(self.ctx.world)]
-        eng.quarter_scatter(self.scratch, m * R * m, n, P, self.img4_scatter, self.c_dtype, m, dests, m, R, 1, m, m * m,
-                            self.r_block, m**3, deal=self.deal)
+        [p_loc][q][r][s]: the result is sharded on its leading index again.  r = rank + W r_loc: this rank's rows
+        of every (r, s) block interleave with the other ranks' rows."""
+        eng, n, m, R, P, W = self.engine, self.n, self.m, self.R, self.P, self.ctx.world
+        dests = [(out[j], self.rank * m) for j in range(W)]
+        eng.quarter_scatter(self.scratch, m * R * m, n, P, self.img4_scatter, self.c_dtype, m, dests, m, R, 1, W * m,
+                            m * m, self.r_block, m**3, deal=self.deal)
 
     # ---- anti-symmetric u: steps 3 and 4 on half of the (r, s) pairs (cyclic rule), packed by pair -------------
     def prepare_pairs(self):
-        """Pair tables of this rank: for every owned r the partners s the cyclic rule assigns to (r, s)."""
+        """Pair tables of this rank: for every owned r the partners s the cyclic-distance rule assigns to (r, s)."""
         import numpy
 
-        m, R, P = self.m, self.R, self.P
-        # shape-dependent only: built and uploaded once per (rank, m, world, P), then reused by every transform
+        m, R, P, W = self.m, self.R, self.P, self.ctx.world
+        # shape-dependent only: built and uploaded once per (rank, n, m, world, P), then reused by every transform
         cache = self.ctx.__dict__.setdefault("_pair_tables", {})
-        key = (self.rank, m, self.ctx.world, P)
+        key = (self.rank, self.n, m, W, P)
         if key in cache:
-            (self.npairs, self.slot_of_rs, self.rs_of_pair, self.slot_of_rs_dev, self.rs_of_pair_dev) = cache[key]
+            (self.npairs, self.step3_tables, self.rs_of_pair, self.rs_of_pair_dev) = cache[key]
             return
-        self.slot_of_rs_dev = self.rs_of_pair_dev = None
-        r = self.r_off[self.rank] + numpy.arange(R, dtype=numpy.int64)[:, None]
+        r = self.r_values()[:, None]
         sI = numpy.arange(m, dtype=numpy.int64)[None, :]
         wanted = cyclic_wanted(r, sI, m)
         self.npairs = int(wanted.sum())
         slot = numpy.full((R, m), -1, dtype=numpy.int64)
         slot[wanted] = numpy.arange(self.npairs, dtype=numpy.int64) * P  # row-major (r_loc, s) order
-        self.slot_of_rs = numpy.ascontiguousarray(slot.reshape(-1))
         self.rs_of_pair = numpy.ascontiguousarray((r * m + sI)[wanted])
+        self.rs_of_pair_dev = self.engine.index_table(self.rs_of_pair) if self.npairs else None
+        # step 3 reads the source-major T2: rows (src, r_loc, s, a_loc) -> T3p[q, pair(r_loc, s), a_off[src] + a_loc]
+        self.step3_tables = []
         if self.npairs:
-            self.slot_of_rs_dev = self.engine.index_table(self.slot_of_rs)
-            self.rs_of_pair_dev = self.engine.index_table(self.rs_of_pair)
-        cache[key] = (self.npairs, self.slot_of_rs, self.rs_of_pair, self.slot_of_rs_dev, self.rs_of_pair_dev)
+            if self.even_sources:
+                per_source = [slot.reshape(-1) + numpy.where(slot.reshape(-1) >= 0, self.a_off[src], 0)
+                              for src in range(W)]
+                table = numpy.ascontiguousarray(numpy.concatenate(per_source))
+                self.step3_tables = [(None, table, self.engine.index_table(table))]
+            else:
+                for src in range(W):
+                    if self.a_off[src + 1] > self.a_off[src]:
+                        table = numpy.ascontiguousarray(slot.reshape(-1) + numpy.where(slot.reshape(-1) >= 0, self.a_off[src], 0))
+                        self.step3_tables.append((src, table, self.engine.index_table(table)))
+        cache[key] = (self.npairs, self.step3_tables, self.rs_of_pair, self.rs_of_pair_dev)
 
     def step3_pairs(self, recv_local):
-        """T3p[q, pair(r_loc, s), a] = sum_b T2[r_loc, s, a, b] C~[q, b] for the wanted pairs only."""
+        """T3p[q, pair(r_loc, s), a] = sum_b T2[src][r_loc][s][a_loc][b] C~[q, b] for the wanted pairs only."""
         eng, n, m, R, P = self.engine, self.n, self.m, self.R, self.P
         if self.npairs == 0:
             return
-        eng.quarter_rows(recv_local, R * m * n, n, P, self.img3, self.c_dtype, m, self.scratch, n, 1, self.slot_of_rs,
-                         self.slot_of_rs_dev, 1, 0, self.npairs * P)
+        for src, host_table, dev_table in self.step3_tables:
+            if src is None:  # all sources in one launch: blocks of A rows, table over (src, r_loc, s)
+                eng.quarter_rows(recv_local, R * m * n, n, P, self.img3, self.c_dtype, m, self.scratch, self.A, 1,
+                                 host_table, dev_table, 1, 0, self.npairs * P)
+            else:
+                A_src = self.a_off[src + 1] - self.a_off[src]
+                block = _slice(recv_local, self.a_off[src] * R * m * P, R * m * A_src * P)
+                eng.quarter_rows(block, R * m * A_src, n, P, self.img3, self.c_dtype, m, self.scratch, A_src, 1,
+                                 host_table, dev_table, 1, 0, self.npairs * P)
 
     def step4_scatter_pairs(self, out):
         """u'[p, q, r, s] = sum_a T3p[q, pair, a] C~[p, a] for the wanted pairs, stored into the rank that owns p."""
@@ -772,7 +834,8 @@ def transform_two_body_sharded(u, C, C_tilde=None, symmetry=None):
         ctx.barrier()  # all tiles of u' have landed
         if symmetry:
             for r, w in work.items():
-                ctx.engine.cyclic_fill(out[r][r], m, w.R)  # the other half of every local plane: -u'[p,q,s,r]
+                # the other half of every local plane p: -u'[p,q,s,r]
+                ctx.engine.cyclic_fill(out[r][r], m, w.r_off[r + 1] - w.r_off[r])
         spare = u.buffers if (u.dtype == t_dtype and m == n) else None
         result = ShardedTwoBody(ctx, m, t_dtype, out, spare)
         result.proven_antisymmetric = bool(symmetry)  # the cyclic fill wrote exact negatives and a zero diagonal

@@ -72,7 +72,7 @@ class NumpyEngine:
         out.flat()[out_offset + ax[:, None] + aw[None, :]] = res
 
     def quarter_scatter(self, A, X, K, lda, image, m_dtype, W, dests, x_inner, x_mid, sx0, sx1, sx2, w_inner, sw0,
-                        deal=1):
+                        deal=1, cyclic=False):
         if X <= 0:
             return
         res = self._product(A, X, K, lda, image)
@@ -85,10 +85,14 @@ class NumpyEngine:
         xq = x // x_inner
         ax = (xq // x_mid) * sx2 + (xq % x_mid) * sx1 + (x % x_inner) * sx0
         for j, (buf, off) in enumerate(dests):
-            cols = np.arange(j * w_inner, min((j + 1) * w_inner, W))
+            if cyclic:  # column w goes to destination w % n_dest and is column w // n_dest there
+                cols = np.arange(j, W, len(dests))
+                aw = (cols // len(dests)) * sw0
+            else:
+                cols = np.arange(j * w_inner, min((j + 1) * w_inner, W))
+                aw = (cols % max(w_inner, 1)) * sw0
             if len(cols) == 0:
                 continue
-            aw = (cols % w_inner) * sw0
             buf.flat()[off + ax[:, None] + aw[None, :]] = res[:, cols]
 
     # consumers of a shard: documented semantics of qs_extract_block / qs_scale_add / qs_occupied_traces

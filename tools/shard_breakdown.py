@@ -24,32 +24,6 @@ def main():
     w.prepare(C, None)
     recv = ctx.shared_cached("recv", [w.recv_numel(r) for r in range(world)], torch.float64)
     out = u.spare
-    # experiment (timing only, the result is then wrong): let rank r write into block position (r + k) % W of every
-    # destination instead of position r -- does the rank-dependent scatter time follow the POSITION written?
-    k = int(os.environ.get("QS_ROTATE_POSITION", "0"))
-    if k:
-        w.a_off = list(w.a_off)
-        w.r_off = list(w.r_off)
-        w.a_off[rank] = ((rank + k) % world) * w.a_block
-        w.r_off[rank] = ((rank + k) % world) * w.r_block
-    # experiment (timing only): change WHERE the scattered tiles land so that the eight write streams into a
-    # destination are not eight adjacent 36 KB chunks of one block --
-    #   step 2: source-major chunks, recv[r_loc][src][s][a_loc][b] (streams m*A*P elements apart)
-    #   step 4: cyclic r inside the [r][s] block of the result (streams interleaved row by row)
-    if os.environ.get("QS_LAYOUT_EXPERIMENT"):
-        eng, P, A, R, m = w.engine, w.P, w.A, w.R, w.m
-
-        def step2_scatter(recv_bufs):
-            dests = [(recv_bufs[j], rank * m * A * P) for j in range(world)]
-            eng.quarter_scatter(w.scratch, m * A * n, n, P, w.img2_scatter, w.c_dtype, m, dests, n, A, 1, P, A * P,
-                                w.r_block, m * n * P, deal=w.deal)
-
-        def step4_scatter(out_bufs):
-            dests = [(out_bufs[j], rank * m) for j in range(world)]
-            eng.quarter_scatter(w.scratch, m * R * m, n, P, w.img4_scatter, w.c_dtype, m, dests, m, R, 1, world * m,
-                                m * m, w.r_block, m**3, deal=w.deal)
-
-        w.step2_scatter, w.step4_scatter = step2_scatter, step4_scatter
     names = ["step1", "step2_scatter", "barrier", "step3", "step4_scatter", "barrier2"]
     acc = {k: [] for k in names}
     for it in range(4):
