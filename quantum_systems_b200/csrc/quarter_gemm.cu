@@ -78,6 +78,10 @@ struct QuarterParams {
     // destinations by themselves, and a rank that owns the cyclic columns writes rows INTERLEAVED with the other
     // ranks' rows later on, never one of W adjacent chunks of a block (see sharded.py, "where the tiles land").
     int w_cyclic;
+    // Rotated tile order (scattering store): the CTAs walk the tiles starting at tile_start (mod the number of
+    // tiles).  Ranks that start at different places do not write into the same block of a destination at the same
+    // time.
+    uint32_t tile_start;
     // Optional tile list (symmetry-aware transforms): when non-null the launch visits only the n_listed linear
     // tile ids (row_tile * tiles_w + col_tile, ascending) stored there instead of all tiles_x * tiles_w tiles.
     const uint32_t* tile_list;
@@ -91,6 +95,15 @@ struct QuarterParams {
 
 __device__ __forceinline__ uint32_t dealt_column(uint32_t w, uint32_t mul, uint32_t mod) {
     return mul == 1 ? w : (uint32_t)(((unsigned long long)w * mul) % mod);
+}
+
+// The k-th tile of this launch: through the optional list, in the optionally rotated order.
+__device__ __forceinline__ uint32_t tile_at(const QuarterParams& p, uint32_t k, uint32_t total) {
+    if (p.tile_start) {
+        k += p.tile_start;
+        if (k >= total) k -= total;
+    }
+    return p.tile_list ? p.tile_list[k] : k;
 }
 
 #ifdef QS_DBG_NOWAIT
@@ -187,7 +200,7 @@ quarter_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             const uint32_t bar_empty = bar_full + 8 * kStages;
             uint32_t j = 0;
             for (uint32_t i = pg; i < my_tiles; i += kGroups) {
-                const uint32_t tile = p.tile_list ? p.tile_list[blockIdx.x + i * gridDim.x] : blockIdx.x + i * gridDim.x;
+                const uint32_t tile = tile_at(p, blockIdx.x + i * gridDim.x, total_tiles);
                 const uint32_t tw = tile % (uint32_t)p.tiles_w;
                 const int px0 = (int)((tile / (uint32_t)p.tiles_w) * kBlockX);
                 const double* img = p.image + (size_t)tw * p.nchunks * (kBTileBytes / 8);
@@ -252,7 +265,7 @@ quarter_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
     uint32_t bulk_pass = 0;  // BULK: staging passes done so far (selects the buffer, bounds the pending copy groups)
     for (uint32_t i = group; i < my_tiles; i += kGroups) {
-        const uint32_t tile = p.tile_list ? p.tile_list[blockIdx.x + i * gridDim.x] : blockIdx.x + i * gridDim.x;
+        const uint32_t tile = tile_at(p, blockIdx.x + i * gridDim.x, total_tiles);
 
         double acc[4][NT][2];
 #pragma unroll
@@ -584,7 +597,7 @@ quarter_gemm_split_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
             const uint32_t bar_empty = bar_full + 8 * kStages;
             uint32_t j = 0;
             for (uint32_t i = pg; i < my_tiles; i += kGroups) {
-                const uint32_t tile = p.tile_list ? p.tile_list[blockIdx.x + i * gridDim.x] : blockIdx.x + i * gridDim.x;
+                const uint32_t tile = tile_at(p, blockIdx.x + i * gridDim.x, total_tiles);
                 const uint32_t tw = tile % (uint32_t)p.tiles_w;
                 const int px0 = (int)((tile / (uint32_t)p.tiles_w) * kBlockX);
                 const double* img = p.image + (size_t)tw * p.nchunks * (kBTileBytes / 8);
@@ -627,7 +640,7 @@ quarter_gemm_split_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
     };
 
     for (uint32_t i = group; i < my_tiles; i += kGroups) {
-        const uint32_t tile = p.tile_list ? p.tile_list[blockIdx.x + i * gridDim.x] : blockIdx.x + i * gridDim.x;
+        const uint32_t tile = tile_at(p, blockIdx.x + i * gridDim.x, total_tiles);
 
         double re[4][NTC][2], im[4][NTC][2];
 #pragma unroll
@@ -1221,7 +1234,8 @@ int quarter_launch(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda
                    int64_t sx0, int64_t sx1, int64_t sx2, int64_t w_inner, int64_t sw0, int64_t sw1, int64_t w_deal,
                    void* stream, const QsTileMask* mask = nullptr, void* list_ws = nullptr,
                    const long long* xq_table = nullptr, const long long* xr_table = nullptr,
-                   const long long* host_xq_table = nullptr, int xq_even = 0, int w_cyclic = 0) {
+                   const long long* host_xq_table = nullptr, int xq_even = 0, int w_cyclic = 0,
+                   int64_t tile_start = 0) {
     QS_REQUIRE(A && image && (out || out_table), "qs_quarter_transform: null pointer");
     QS_REQUIRE(w_deal >= 1 && w_deal < (W > 1 ? W : 2) && gcd64(w_deal, W) == 1,
                "qs_quarter_transform_scatter: the dealing multiplier %lld is not coprime to W = %lld",
@@ -1348,6 +1362,10 @@ int quarter_launch(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda
         p.deal_mul = (uint32_t)w_deal;
         p.deal_mod = (uint32_t)W;
         p.w_cyclic = w_cyclic;
+        {   // rotation of the tile order, as a fraction of this group's tiles (tile_start is given in 1/65536)
+            const int64_t total = p.tile_list ? (int64_t)p.n_listed : (int64_t)p.tiles_x * p.tiles_w;
+            p.tile_start = (uint32_t)((total * (tile_start & 0xFFFF)) >> 16);
+        }
         p.xq_table = xq_table;
         p.xr_table = xr_table;
         QS_REQUIRE((int64_t)p.tiles_x * p.tiles_w < (1LL << 31), "qs_quarter_transform: too many tiles");
@@ -1440,11 +1458,12 @@ extern "C" int qs_quarter_transform_scatter_rows(const void* A, int a_dtype, int
                                                  const void* image, int m_dtype, int64_t W,
                                                  void* const* host_out_table, int64_t n_dest, int64_t x_inner,
                                                  int64_t sx1, const int64_t* xr_table, int64_t w_inner, int64_t sw0,
-                                                 int64_t w_deal, void* stream) {
+                                                 int64_t w_deal, int64_t tile_start, void* stream) {
     QS_REQUIRE(host_out_table && n_dest > 0 && xr_table, "qs_quarter_transform_scatter_rows: null pointer");
+    QS_REQUIRE(tile_start >= 0 && tile_start < 65536, "qs_quarter_transform_scatter_rows: tile_start is a fraction in 1/65536");
     return quarter_launch(A, a_dtype, X, K, lda, image, m_dtype, W, nullptr, host_out_table, n_dest, x_inner,
                           0xFFFFFFFFLL, 0, sx1, 0, w_inner, sw0, 0, w_deal, stream, nullptr, nullptr, nullptr,
-                          reinterpret_cast<const long long*>(xr_table));
+                          reinterpret_cast<const long long*>(xr_table), nullptr, 0, 0, tile_start);
 }
 
 extern "C" int qs_quarter_transform(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda, const void* image,
@@ -1458,9 +1477,10 @@ extern "C" int qs_quarter_transform_scatter(const void* A, int a_dtype, int64_t 
                                             const void* image, int m_dtype, int64_t W, void* const* host_out_table,
                                             int64_t n_dest, int64_t x_inner, int64_t x_mid, int64_t sx0, int64_t sx1,
                                             int64_t sx2, int64_t w_inner, int64_t sw0, int64_t w_deal,
-                                            int w_cyclic, void* stream) {
+                                            int w_cyclic, int64_t tile_start, void* stream) {
     QS_REQUIRE(host_out_table && n_dest > 0, "qs_quarter_transform_scatter: empty destination table");
+    QS_REQUIRE(tile_start >= 0 && tile_start < 65536, "qs_quarter_transform_scatter: tile_start is a fraction in 1/65536");
     return quarter_launch(A, a_dtype, X, K, lda, image, m_dtype, W, nullptr, host_out_table, n_dest, x_inner, x_mid, sx0,
                           sx1, sx2, w_inner, sw0, 0, w_deal, stream, nullptr, nullptr, nullptr, nullptr, nullptr, 0,
-                          w_cyclic);
+                          w_cyclic, tile_start);
 }

@@ -53,6 +53,14 @@ def block_partition(n, world):
 SYMMETRY_MIN_N = 48
 # False: `transform_two_body_sharded(symmetry=None)` never tests for anti-symmetry and runs the four full quarter steps
 EXPLOIT_SYMMETRY = True
+# Where the scattered tiles land in the peer schedule (see _RankTransform): "source_major" = cyclic intermediate index
+# and source-major T2; "interleaved" = block partition of r and T2[r_loc][s][a][b] (the round-1 layout).
+# ROTATE_TILES: every rank starts its walk over the tiles of a scattering launch at a different place (rank / world
+# of the way through), so that the ranks are never in the same block of a destination at the same time.
+import os as _os
+
+SCATTER_LAYOUT = _os.environ.get("QS_SHARD_LAYOUT", "source_major")
+ROTATE_TILES = _os.environ.get("QS_SHARD_ROTATE", "0") == "1"
 
 
 def cyclic_wanted(r, s, m):
@@ -177,14 +185,14 @@ class CudaEngine:
         lists.record_stream(torch.cuda.current_stream())
 
     def quarter_scatter_rows(self, A, X, K, lda, image, m_dtype, W, dests, x_inner, sx1, xr_table, w_inner, sw0,
-                             deal=1):
+                             deal=1, tile_start=0):
         if X <= 0:
             return
         table = (ctypes.c_void_p * len(dests))(*[buf.at(off) for buf, off in dests])
         _native.call(
             "qs_quarter_transform_scatter_rows", ctypes.c_void_p(A.at(0)), _CODES[A.dtype], X, K, lda,
             ctypes.c_void_p(image.data_ptr()), _CODES[m_dtype], W, table, len(dests), x_inner, sx1,
-            ctypes.c_void_p(xr_table.data_ptr()), w_inner, sw0, int(deal), self._stream(),
+            ctypes.c_void_p(xr_table.data_ptr()), w_inner, sw0, int(deal), int(tile_start), self._stream(),
         )
 
     # consumers of a shard (csrc/consumers.cu)
@@ -216,14 +224,14 @@ class CudaEngine:
         return out
 
     def quarter_scatter(self, A, X, K, lda, image, m_dtype, W, dests, x_inner, x_mid, sx0, sx1, sx2, w_inner, sw0,
-                        deal=1, cyclic=False):
+                        deal=1, cyclic=False, tile_start=0):
         if X <= 0:
             return
         table = (ctypes.c_void_p * len(dests))(*[buf.at(off) for buf, off in dests])
         _native.call(
             "qs_quarter_transform_scatter", ctypes.c_void_p(A.at(0)), _CODES[A.dtype], X, K, lda,
             ctypes.c_void_p(image.data_ptr()), _CODES[m_dtype], W, table, len(dests), x_inner, max(x_mid, 1), sx0, sx1,
-            sx2, max(w_inner, 1), sw0, int(deal), int(bool(cyclic)), self._stream(),
+            sx2, max(w_inner, 1), sw0, int(deal), int(bool(cyclic)), int(tile_start), self._stream(),
         )
 
 
@@ -579,7 +587,8 @@ class _RankTransform:
         self.a_block, self.a_off = block_partition(n, ctx.world)  # partition of the old leading index
         self.r_block, self.r_off = block_partition(m, ctx.world)  # partition of the new leading index p (and of r
         #                                                           in the collective schedule)
-        self.cyclic = ctx.exchange == "peer"                       # peer schedule: r is dealt cyclically
+        self.cyclic = ctx.exchange == "peer" and SCATTER_LAYOUT == "source_major"  # r dealt cyclically
+        self.tile_start = (rank * 65536) // ctx.world if (ROTATE_TILES and ctx.exchange == "peer") else 0
         self.Pu = padded_pitch(n, u_dtype)
         self.P = padded_pitch(n, self.t_dtype)
         self.A = self.a_off[rank + 1] - self.a_off[rank]
@@ -623,6 +632,9 @@ class _RankTransform:
         # its output columns over all destinations (uniform NVLink traffic): its image holds the columns of C~ in
         # dealt order.  The first exchange sends cyclic columns and needs no dealing.
         self.deal = eng.scatter_deal(m) if self.ctx.exchange == "peer" and self.ctx.world > 1 else 1
+        self.img2_scatter = self.img2
+        if self.deal > 1 and not self.cyclic:  # block partition of r: the first exchange deals its columns too
+            self.img2_scatter = eng.image(C, n, m, self.t_dtype, m, 1, deal=self.deal)
         if self.deal > 1:
             if C_tilde is not None:
                 self.img4_scatter = eng.image(C_tilde, n, m, self.t_dtype, 1, n, deal=self.deal)
@@ -650,10 +662,15 @@ class _RankTransform:
         and this rank's tiles fill ONE contiguous region of every destination."""
         eng, n, m, A, P = self.engine, self.n, self.m, self.A, self.P
         a0 = self.a_off[self.rank]
+        if not self.cyclic:  # interleaved layout: [r_loc][s][a][b], this rank's planes between the others'
+            dests = [(recv[j], a0 * P) for j in range(self.ctx.world)]
+            eng.quarter_scatter(self.scratch, m * A * n, n, P, self.img2_scatter, self.c_dtype, m, dests, n, A, 1, P,
+                                n * P, self.r_block, m * n * P, deal=self.deal, tile_start=self.tile_start)
+            return
         # region of this source in destination j: behind the regions of the sources before it
         dests = [(recv[j], a0 * self.r_count(j) * m * P) for j in range(self.ctx.world)]
         eng.quarter_scatter(self.scratch, m * A * n, n, P, self.img2, self.c_dtype, m, dests, n, A, 1, P, A * P,
-                            0, m * A * P, deal=1, cyclic=True)
+                            0, m * A * P, deal=1, cyclic=True, tile_start=self.tile_start)
 
     def step2_local(self, send):
         """Collective schedule: T2[r, s, a_loc, b] written locally, blocks of r contiguous per destination."""
@@ -667,7 +684,9 @@ class _RankTransform:
         eng, n, m, R, P = self.engine, self.n, self.m, self.R, self.P
         if R == 0:
             return
-        if self.even_sources:
+        if not self.cyclic:  # interleaved layout: rows (r_loc, s, a) in place
+            eng.quarter(recv_local, R * m * n, n, P, self.img3, self.c_dtype, m, self.scratch, 0, n, 1, P, 1, 0, R * m * P)
+        elif self.even_sources:
             eng.quarter_scatter(recv_local, R * m * n, n, P, self.img3, self.c_dtype, m, [(self.scratch, 0)], self.A,
                                 R * m, 1, P, self.A, m, R * m * P, deal=1)
         else:
@@ -692,9 +711,14 @@ class _RankTransform:
         [p_loc][q][r][s]: the result is sharded on its leading index again.  r = rank + W r_loc: this rank's rows
         of every (r, s) block interleave with the other ranks' rows."""
         eng, n, m, R, P, W = self.engine, self.n, self.m, self.R, self.P, self.ctx.world
+        if not self.cyclic:  # block partition of r: this rank's rows are one chunk of every (r, s) block
+            dests = [(out[j], self.r_off[self.rank] * m) for j in range(W)]
+            eng.quarter_scatter(self.scratch, m * R * m, n, P, self.img4_scatter, self.c_dtype, m, dests, m, R, 1, m,
+                                m * m, self.r_block, m**3, deal=self.deal, tile_start=self.tile_start)
+            return
         dests = [(out[j], self.rank * m) for j in range(W)]
         eng.quarter_scatter(self.scratch, m * R * m, n, P, self.img4_scatter, self.c_dtype, m, dests, m, R, 1, W * m,
-                            m * m, self.r_block, m**3, deal=self.deal)
+                            m * m, self.r_block, m**3, deal=self.deal, tile_start=self.tile_start)
 
     # ---- anti-symmetric u: steps 3 and 4 on half of the (r, s) pairs (cyclic rule), packed by pair -------------
     def prepare_pairs(self):
@@ -704,7 +728,7 @@ class _RankTransform:
         m, R, P, W = self.m, self.R, self.P, self.ctx.world
         # shape-dependent only: built and uploaded once per (rank, n, m, world, P), then reused by every transform
         cache = self.ctx.__dict__.setdefault("_pair_tables", {})
-        key = (self.rank, self.n, m, W, P)
+        key = (self.rank, self.n, m, W, P, self.cyclic)
         if key in cache:
             (self.npairs, self.step3_tables, self.rs_of_pair, self.rs_of_pair_dev) = cache[key]
             return
@@ -719,7 +743,10 @@ class _RankTransform:
         # step 3 reads the source-major T2: rows (src, r_loc, s, a_loc) -> T3p[q, pair(r_loc, s), a_off[src] + a_loc]
         self.step3_tables = []
         if self.npairs:
-            if self.even_sources:
+            if not self.cyclic:  # interleaved layout: rows (r_loc, s, a), blocks of n rows
+                table = numpy.ascontiguousarray(slot.reshape(-1))
+                self.step3_tables = [("interleaved", table, self.engine.index_table(table))]
+            elif self.even_sources:
                 per_source = [slot.reshape(-1) + numpy.where(slot.reshape(-1) >= 0, self.a_off[src], 0)
                               for src in range(W)]
                 table = numpy.ascontiguousarray(numpy.concatenate(per_source))
@@ -737,7 +764,10 @@ class _RankTransform:
         if self.npairs == 0:
             return
         for src, host_table, dev_table in self.step3_tables:
-            if src is None:  # all sources in one launch: blocks of A rows, table over (src, r_loc, s)
+            if src == "interleaved":
+                eng.quarter_rows(recv_local, R * m * n, n, P, self.img3, self.c_dtype, m, self.scratch, n, 1,
+                                 host_table, dev_table, 1, 0, self.npairs * P)
+            elif src is None:  # all sources in one launch: blocks of A rows, table over (src, r_loc, s)
                 eng.quarter_rows(recv_local, R * m * n, n, P, self.img3, self.c_dtype, m, self.scratch, self.A, 1,
                                  host_table, dev_table, 1, 0, self.npairs * P)
             else:
@@ -753,7 +783,8 @@ class _RankTransform:
             return
         dests = [(out[j], 0) for j in range(self.ctx.world)]
         eng.quarter_scatter_rows(self.scratch, m * self.npairs, n, P, self.img4_scatter, self.c_dtype, m, dests,
-                                 self.npairs, m * m, self.rs_of_pair_dev, self.r_block, m**3, deal=self.deal)
+                                 self.npairs, m * m, self.rs_of_pair_dev, self.r_block, m**3, deal=self.deal,
+                                 tile_start=self.tile_start)
 
     def step4_local(self, out_local):
         """Collective schedule: u'[p, q, r_loc, s] dense on this rank (sharded on the third index)."""

@@ -72,7 +72,7 @@ class NumpyEngine:
         out.flat()[out_offset + ax[:, None] + aw[None, :]] = res
 
     def quarter_scatter(self, A, X, K, lda, image, m_dtype, W, dests, x_inner, x_mid, sx0, sx1, sx2, w_inner, sw0,
-                        deal=1, cyclic=False):
+                        deal=1, cyclic=False, tile_start=0):
         if X <= 0:
             return
         res = self._product(A, X, K, lda, image)
@@ -150,7 +150,8 @@ class NumpyEngine:
         aw = (w // w_inner) * sw1 + (w % w_inner) * sw0
         out.flat()[ax[:, None] + aw[None, :]] = res[keep]
 
-    def quarter_scatter_rows(self, A, X, K, lda, image, m_dtype, W, dests, x_inner, sx1, xr_table, w_inner, sw0, deal=1):
+    def quarter_scatter_rows(self, A, X, K, lda, image, m_dtype, W, dests, x_inner, sx1, xr_table, w_inner, sw0, deal=1,
+                             tile_start=0):
         if X <= 0:
             return
         res = self._product(A, X, K, lda, image)

@@ -186,3 +186,52 @@ def test_emulated_symmetry_aware_sharded_transform(world, n, m, u_complex, c_com
     np.testing.assert_array_equal(got, -got.transpose(0, 1, 3, 2))  # the mirror image is a copy
     plain = sharded.transform_two_body_sharded(basis.u, dev(C), None if Ct is None else dev(Ct), symmetry=0)
     assert_close_scaled(plain.gather().cpu().numpy(), expected, rel=1e-12)
+
+
+@pytest.mark.parametrize("world,complex_", [(4, False), (3, True)])
+def test_sharded_odqd_general_system_against_the_closed_form(world, complex_):
+    """The pipeline of BASELINE configs[3]/[4] in miniature (emulated ranks): ShardedBasisSet.from_odqd (sharded grid
+    build -> add_spin + anti-symmetrise) -> change_basis twice -> Fock matrix, checked against the closed form of
+    the ODQD-structured tensor (tests/closed_form.py) exactly as bench.py checks the full-size runs, and against
+    the oracle's explicit pipeline."""
+    import closed_form
+    from quantum_systems_b200 import sharded
+    from quantum_systems_b200.potentials import HOPotential
+
+    l, G = 26, 105
+    n = 2 * l
+    dtype = torch.complex128 if complex_ else torch.float64
+    ctx = sharded.EmulatedContext(world)
+    basis = sharded.ShardedBasisSet.from_odqd(ctx, l, 8.0, G, potential=HOPotential(0.5), out_dtype=dtype)
+    assert basis.u.proven_antisymmetric and basis.includes_spin and basis.l == n
+    rng = np.random.default_rng(world)
+    if complex_:
+        C = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)) + 4 * np.eye(n)
+        Ct = np.linalg.inv(C)
+    else:
+        C, Ct = np.linalg.qr(rng.standard_normal((n, n)))[0], None
+    W = closed_form.shielded_coulomb(basis.inner_grid, 1.0, 0.25)
+    # explicit reference pipeline at this size
+    grid, eps, Lg = oracle.odqd_orbitals(l, 8.0, G, HOPotential(0.5))
+    np.testing.assert_allclose(np.abs(Lg), np.abs(basis.grid_coefficients), atol=1e-12)
+    spin = oracle.anti_symmetrize_u(oracle.add_spin_two_body(np.ascontiguousarray(
+        oracle.odqd_coulomb_elements(basis.grid_coefficients, grid, 1.0, 0.25))))
+    assert_close_scaled(basis.u.gather().cpu().numpy(), spin.astype(np.complex128 if complex_ else np.float64))
+
+    basis.change_basis(dev(C), None if Ct is None else dev(Ct))
+    form = closed_form.SpinDoubledClosedForm(basis.grid_coefficients, W, C, Ct)
+    for r in range(world):
+        p0, p1 = basis.u.planes(r)
+        errs = closed_form.check_shard(closed_form.TorchSlab(basis.u.local(r)), p0, form, np.random.default_rng(r), samples=500)
+        assert max(errs[:2]) <= 1e-12 * errs[3] and errs[2] == 0.0
+    assert_close_scaled(basis.u.gather().cpu().numpy(), oracle.transform_two_body_elements(spin, C, Ct))
+    # second call of the chain: no new symmetry test, net transform C C / C~ C~
+    basis.change_basis(dev(C), None if Ct is None else dev(Ct))
+    Ct1 = C.conj().T if Ct is None else Ct
+    net = closed_form.SpinDoubledClosedForm(basis.grid_coefficients, W, C @ C, Ct1 @ Ct1)
+    errs = closed_form.check_shard(closed_form.TorchSlab(basis.u.local(0)), 0, net, np.random.default_rng(7), samples=500)
+    assert max(errs[:2]) <= 1e-11 * errs[3]
+    n_occ = 6
+    f = basis.construct_fock_matrix(basis.h, basis.u, n_occ).cpu().numpy()
+    ref_f = basis.h.cpu().numpy() + net.fock_two_body(n_occ)
+    assert_close_scaled(f, ref_f, rel=1e-11)
