@@ -171,7 +171,10 @@ int qs_transform_two_body_diagonal(const void* w2d, int w_dtype, const void* C, 
  *       xq_table; list_ws: qs_quarter_tile_list_bytes() bytes of device memory).
  *   qs_quarter_transform_scatter_rows : the scattering store with row x at xq * sx1 + xr_table[xr] inside the
  *       destination buffer chosen by the column (see qs_quarter_transform_scatter).
- * Tables are int64 element offsets in device memory. */
+ * Tables are int64 element offsets in device memory.  `rows_paired` != 0 is the caller's promise that the row table
+ * places rows 2k and 2k + 1 next to each other at an even offset (xr_table[2k + 1] = xr_table[2k] + 1, xr_table[2k]
+ * even): a real result is then stored in 16-byte pairs forming whole 128-byte lines -- over NVLink that is the
+ * difference between 8-byte and full-line writes.  qs_quarter_transform_rows checks its (host) block table itself. */
 int qs_quarter_tile_list_bytes(int64_t X, int64_t K, int64_t W, int a_dtype, int m_dtype, int64_t* bytes);
 /* Host-only planning of a masked launch (no device is touched): the CTA tiles it would visit, as rows of
  * (first row, last row, first output column, last output column) in host_tiles (capacity rows of 4 int64; may be
@@ -191,7 +194,8 @@ int qs_quarter_transform_scatter_rows(const void* A, int a_dtype, int64_t X, int
                                       const void* image, int m_dtype, int64_t W,
                                       void* const* host_out_table, int64_t n_dest, int64_t x_inner,
                                       int64_t sx1, const int64_t* xr_table, int64_t w_inner,
-                                      int64_t sw0, int64_t w_deal, int64_t tile_start, void* stream);
+                                      int64_t sw0, int64_t w_deal, int64_t tile_start, int rows_paired,
+                                      void* stream);
 
 /* Copy `rows` rows of n elements into rows of `pitch` >= n elements, zero-filling the tail (real
  * tensors with odd n need an even pitch before they can be described to TMA). */

@@ -80,7 +80,8 @@ int64_t qs_tile_list_bytes(int64_t X, int64_t K, int64_t W, int a_dtype, int m_d
 int qs_quarter_transform_masked(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda, const void* image,
                                 int m_dtype, int64_t W, void* out, int64_t x_inner, int64_t sx0, int64_t sx1,
                                 int64_t w_inner, int64_t sw0, int64_t sw1, const QsTileMask* mask, void* list_ws,
-                                const long long* xq_table, const long long* xr_table, int xq_even, void* stream);
+                                const long long* xq_table, const long long* xr_table, int xq_even, int xr_paired,
+                                void* stream);
 
 int qs_mirror_fill(void* out, int dtype, int64_t m, int mode, void* stream);
 

@@ -1235,7 +1235,7 @@ int quarter_launch(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda
                    void* stream, const QsTileMask* mask = nullptr, void* list_ws = nullptr,
                    const long long* xq_table = nullptr, const long long* xr_table = nullptr,
                    const long long* host_xq_table = nullptr, int xq_even = 0, int w_cyclic = 0,
-                   int64_t tile_start = 0) {
+                   int64_t tile_start = 0, int xr_paired = 0) {
     QS_REQUIRE(A && image && (out || out_table), "qs_quarter_transform: null pointer");
     QS_REQUIRE(w_deal >= 1 && w_deal < (W > 1 ? W : 2) && gcd64(w_deal, W) == 1,
                "qs_quarter_transform_scatter: the dealing multiplier %lld is not coprime to W = %lld",
@@ -1280,20 +1280,23 @@ int quarter_launch(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda
         return QS_ERR_CUDA;
     }
 
-    // 16-byte row-pair stores of the real epilogue need adjacent, aligned rows and even strides everywhere
-    int vec2 = !out_complex && sx0 == 1 && x_inner % 2 == 0 && X % 2 == 0 && sx1 % 2 == 0 && sx2 % 2 == 0 &&
-               sw0 % 2 == 0 && (n_dest > 0 || sw1 % 2 == 0) && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
-    for (int64_t d = 0; d < n_dest; ++d) vec2 = vec2 && (reinterpret_cast<uintptr_t>(out_table[d]) & 15) == 0;
-    if (xq_table || xr_table) vec2 = 0;  // tabulated row offsets: adjacent rows need not be adjacent in memory
-    // Staged asynchronous epilogue: consecutive rows of a block are adjacent in the output (sx0 = 1) and every run of
-    // rows handed to cp.async.bulk starts 16-byte aligned: always for complex output (16-byte elements); for real
-    // output when all extents, strides and bases are even (the conditions of vec2), with an even row table.
-    // Rows placed one by one (xr_table) keep the register stores.
     if (host_xq_table) {  // the caller's own table: every kept entry must be even for 16-byte aligned real runs
         xq_even = 1;
         for (int64_t q = 0, nq = qs_ceil_div(X, x_inner); q < nq && xq_even; ++q)
             xq_even = host_xq_table[q] < 0 || host_xq_table[q] % 2 == 0;
     }
+    // 16-byte row-pair stores of the real epilogue need adjacent, aligned rows and even strides everywhere.  With
+    // tabulated offsets that is the table's business: block offsets (xq_table) must be even, and a per-row table
+    // (xr_table) must place rows 2k and 2k + 1 next to each other at an even offset (`xr_paired`, the caller's promise).
+    const bool rows_adjacent = xr_table ? xr_paired != 0 : sx0 == 1;
+    int vec2 = !out_complex && rows_adjacent && x_inner % 2 == 0 && X % 2 == 0 && sx1 % 2 == 0 && sx2 % 2 == 0 &&
+               sw0 % 2 == 0 && (n_dest > 0 || sw1 % 2 == 0) && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+               (!xq_table || xq_even);
+    for (int64_t d = 0; d < n_dest; ++d) vec2 = vec2 && (reinterpret_cast<uintptr_t>(out_table[d]) & 15) == 0;
+    // Staged asynchronous epilogue: consecutive rows of a block are adjacent in the output (sx0 = 1) and every run of
+    // rows handed to cp.async.bulk starts 16-byte aligned: always for complex output (16-byte elements); for real
+    // output when all extents, strides and bases are even (the conditions of vec2), with an even row table.
+    // Rows placed one by one (xr_table) keep the register stores.
     int bulk = (bulk_mode() == 2 || (bulk_mode() == 1 && n_dest > 1)) && sx0 == 1 && !xr_table && !tl.split;
     if (bulk && !out_complex) {
         bulk = x_inner % 2 == 0 && X % 2 == 0 && sx1 % 2 == 0 && sx2 % 2 == 0 && sw0 % 2 == 0 &&
@@ -1393,9 +1396,11 @@ int64_t qs_tile_list_bytes(int64_t X, int64_t K, int64_t W, int a_dtype, int m_d
 int qs_quarter_transform_masked(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda, const void* image,
                                 int m_dtype, int64_t W, void* out, int64_t x_inner, int64_t sx0, int64_t sx1,
                                 int64_t w_inner, int64_t sw0, int64_t sw1, const QsTileMask* mask, void* list_ws,
-                                const long long* xq_table, const long long* xr_table, int xq_even, void* stream) {
+                                const long long* xq_table, const long long* xr_table, int xq_even, int xr_paired,
+                                void* stream) {
     return quarter_launch(A, a_dtype, X, K, lda, image, m_dtype, W, out, nullptr, 0, x_inner, 0xFFFFFFFFLL, sx0, sx1, 0,
-                          w_inner, sw0, sw1, 1, stream, mask, list_ws, xq_table, xr_table, nullptr, xq_even);
+                          w_inner, sw0, sw1, 1, stream, mask, list_ws, xq_table, xr_table, nullptr, xq_even, 0, 0,
+                          xr_paired);
 }
 
 // Host-only: the tiles a masked quarter transform would launch, as rows of (first row, last row, first output
@@ -1458,12 +1463,13 @@ extern "C" int qs_quarter_transform_scatter_rows(const void* A, int a_dtype, int
                                                  const void* image, int m_dtype, int64_t W,
                                                  void* const* host_out_table, int64_t n_dest, int64_t x_inner,
                                                  int64_t sx1, const int64_t* xr_table, int64_t w_inner, int64_t sw0,
-                                                 int64_t w_deal, int64_t tile_start, void* stream) {
+                                                 int64_t w_deal, int64_t tile_start, int rows_paired,
+                                                 void* stream) {
     QS_REQUIRE(host_out_table && n_dest > 0 && xr_table, "qs_quarter_transform_scatter_rows: null pointer");
     QS_REQUIRE(tile_start >= 0 && tile_start < 65536, "qs_quarter_transform_scatter_rows: tile_start is a fraction in 1/65536");
     return quarter_launch(A, a_dtype, X, K, lda, image, m_dtype, W, nullptr, host_out_table, n_dest, x_inner,
                           0xFFFFFFFFLL, 0, sx1, 0, w_inner, sw0, 0, w_deal, stream, nullptr, nullptr, nullptr,
-                          reinterpret_cast<const long long*>(xr_table), nullptr, 0, 0, tile_start);
+                          reinterpret_cast<const long long*>(xr_table), nullptr, 0, 0, tile_start, rows_paired);
 }
 
 extern "C" int qs_quarter_transform(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda, const void* image,

@@ -48,7 +48,7 @@ int make_plan(int64_t n, int64_t m, int u_dtype, int c_dtype, TwoBodyPlan* plan)
     lists = lists > l4 ? lists : l4;
     plan->list_bytes = qs_round_up(lists, 1024);
     // row-offset tables of the packed pair layout: m^2 entries (step 3 rows -> pair slot) + m(m+1)/2 (pair -> r m + s)
-    plan->table_bytes = qs_round_up((m * m + m * (m + 1) / 2) * (int64_t)sizeof(long long), 1024);
+    plan->table_bytes = qs_round_up((m * m + m * (m + 1) / 2 + m) * (int64_t)sizeof(long long), 1024);
     // images: [C for step 1][C for step 2][Ct^T for steps 3, 4]
     plan->total = plan->pad_bytes + plan->bufA_bytes + plan->bufB_bytes + plan->img_bytes[0] + 2 * plan->img_bytes[1] +
                   plan->list_bytes + plan->table_bytes;
@@ -91,8 +91,101 @@ int masked_rotated_quarter(const void* A, int a_dtype, int64_t X, int64_t K, int
                            const QsTileMask* mask, void* list_ws, void* stream) {
     const int64_t plane = X / lo_extent * lo_pitch;
     return qs_quarter_transform_masked(A, a_dtype, X, K, lda, image, m_dtype, W, out, lo_extent, 1, lo_pitch, 1, 0,
-                                       plane, mask, list_ws, nullptr, nullptr, 0, stream);
+                                       plane, mask, list_ws, nullptr, nullptr, 0, 0, stream);
 }
+
+// ---------------------------------------------------------------------------------------------
+// One-body matrices (n x n, a few hundred KB): out = Ct (h C).  Through the persistent quarter GEMM each of the two
+// products is a single 128-row tile -- one or two CTAs, a 25 us latency chain per launch next to 3 us of image
+// building -- so small matrices take a plain shared-memory tiled FP64 kernel instead: every 32 x 32 output tile is
+// a CTA, the whole chip works on one product for a few microseconds.
+//   D[i, j] = sum_k opA(A)[i, k] * B[k, j],   opA(A)[i, k] = A[i * sa_i + k * sa_k], optionally conjugated
+// ---------------------------------------------------------------------------------------------
+template <bool A_COMPLEX, bool B_COMPLEX>
+__global__ void __launch_bounds__(256) small_matmul_kernel(const double* __restrict__ A, long long sa_i, long long sa_k,
+                                                           int conj_a, const double* __restrict__ B, int ldb,
+                                                           double* __restrict__ D, int ldd, int I, int J, int K) {
+    constexpr bool D_COMPLEX = A_COMPLEX || B_COMPLEX;
+    __shared__ double ar[32][33], ai[A_COMPLEX ? 32 : 1][33], br[32][33], bi[B_COMPLEX ? 32 : 1][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8 threads, 4 output rows each
+    const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+    double dr[4] = {0, 0, 0, 0}, di[4] = {0, 0, 0, 0};
+    for (int k0 = 0; k0 < K; k0 += 32) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int row = ty + 8 * r;
+            // A tile: element (i0 + row, k0 + tx)
+            double vr = 0.0, vi = 0.0;
+            if (i0 + row < I && k0 + tx < K) {
+                const long long at = (long long)(i0 + row) * sa_i + (long long)(k0 + tx) * sa_k;
+                if (A_COMPLEX) {
+                    const double2 v = reinterpret_cast<const double2*>(A)[at];
+                    vr = v.x;
+                    vi = conj_a ? -v.y : v.y;
+                } else {
+                    vr = A[at];
+                }
+            }
+            ar[row][tx] = vr;
+            if (A_COMPLEX) ai[row][tx] = vi;
+            // B tile: element (k0 + row, j0 + tx)
+            vr = 0.0, vi = 0.0;
+            if (k0 + row < K && j0 + tx < J) {
+                const long long at = (long long)(k0 + row) * ldb + j0 + tx;
+                if (B_COMPLEX) {
+                    const double2 v = reinterpret_cast<const double2*>(B)[at];
+                    vr = v.x;
+                    vi = v.y;
+                } else {
+                    vr = B[at];
+                }
+            }
+            br[row][tx] = vr;
+            if (B_COMPLEX) bi[row][tx] = vi;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) {
+            const double b_r = br[k][tx], b_i = B_COMPLEX ? bi[k][tx] : 0.0;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const double a_r = ar[ty + 8 * r][k], a_i = A_COMPLEX ? ai[ty + 8 * r][k] : 0.0;
+                dr[r] = fma(a_r, b_r, dr[r]);
+                if (A_COMPLEX && B_COMPLEX) dr[r] = fma(-a_i, b_i, dr[r]);
+                if (B_COMPLEX) di[r] = fma(a_r, b_i, di[r]);
+                if (A_COMPLEX) di[r] = fma(a_i, b_r, di[r]);
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int i = i0 + ty + 8 * r, j = j0 + tx;
+        if (i < I && j < J) {
+            if (D_COMPLEX) reinterpret_cast<double2*>(D)[(long long)i * ldd + j] = make_double2(dr[r], di[r]);
+            else D[(long long)i * ldd + j] = dr[r];
+        }
+    }
+}
+
+int small_matmul(const void* A, int a_dtype, int64_t sa_i, int64_t sa_k, int conj_a, const void* B, int b_dtype, int64_t ldb,
+                 void* D, int64_t ldd, int64_t I, int64_t J, int64_t K, void* stream) {
+    const dim3 grid((unsigned)qs_ceil_div(J, 32), (unsigned)qs_ceil_div(I, 32));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const double* a = static_cast<const double*>(A);
+    const double* b = static_cast<const double*>(B);
+    double* d = static_cast<double*>(D);
+    const bool ac = a_dtype == QS_C128, bc = b_dtype == QS_C128;
+    if (ac && bc) small_matmul_kernel<true, true><<<grid, 256, 0, st>>>(a, sa_i, sa_k, conj_a, b, (int)ldb, d, (int)ldd, (int)I, (int)J, (int)K);
+    else if (ac) small_matmul_kernel<true, false><<<grid, 256, 0, st>>>(a, sa_i, sa_k, conj_a, b, (int)ldb, d, (int)ldd, (int)I, (int)J, (int)K);
+    else if (bc) small_matmul_kernel<false, true><<<grid, 256, 0, st>>>(a, sa_i, sa_k, conj_a, b, (int)ldb, d, (int)ldd, (int)I, (int)J, (int)K);
+    else small_matmul_kernel<false, false><<<grid, 256, 0, st>>>(a, sa_i, sa_k, conj_a, b, (int)ldb, d, (int)ldd, (int)I, (int)J, (int)K);
+    QS_LAUNCH_CHECK();
+    return QS_OK;
+}
+
+// below this extent a one-body transform takes the small-matrix kernel (two launches, no images)
+constexpr int64_t kSmallOneBody = 1024;
 
 }  // namespace
 
@@ -174,19 +267,30 @@ extern "C" int qs_transform_two_body_symmetric(const void* u, int u_dtype, const
     // Wanted pairs (r, s), r < s or r <= s, numbered row-major: T3 is kept PACKED by pair, T3p[q, pair, a], so that
     // step 4 is a dense GEMM over m * npairs rows (in the plain layout its 128-row tiles would span the whole
     // range of s and none could be skipped).
-    // The tables depend on (M, P, strict) only: built once per device and kept in device memory (qs_table_cache_*).
-    const int64_t npairs = strict ? M * (M - 1) / 2 : M * (M + 1) / 2;
+    // Real results with an even extent pad every row r of the pair list to whole aligned couples (s even, s + 1): the
+    // list of r then starts at the even s at or below its first wanted partner -- one extra element per other r, the
+    // diagonal (r, r) or the below-diagonal (r, r - 1), which the mirror fill overwrites afterwards.  Rows 2k and
+    // 2k + 1 of step 4 are then neighbours in the result and leave the SM as one 16-byte store (whole 128-byte lines
+    // per quarter warp) instead of two scattered 8-byte ones.
+    const bool paired = td == QS_F64 && M % 2 == 0;
+    auto first_s = [&](int64_t r) {
+        const int64_t s0 = strict ? r + 1 : r;
+        return paired ? (s0 & ~(int64_t)1) : s0;
+    };
+    int64_t npairs = 0;
+    for (int64_t r = 0; r < M; ++r) npairs += M - first_s(r);
     if (npairs == 0) return qs_mirror_fill(out, td, M, symmetry, stream);  // m = 1, antisymmetric: everything is zero
-    struct { int64_t tag, M, P, strict; } table_key = {0x7ab1e, M, P, strict};
+    // The tables depend on (M, P, strict, paired) only: built once per device and kept in device memory.
+    struct { int64_t tag, M, P, strict, paired; } table_key = {0x7ab1e, M, P, strict, paired};
     const long long* dev_tables = static_cast<const long long*>(qs_table_cache_get(&table_key, sizeof(table_key)));
     if (!dev_tables) {
-        std::vector<long long> host_tables((size_t)(M * M + M * (M + 1) / 2));
+        std::vector<long long> host_tables((size_t)(M * M + npairs));
         long long* slot_of_rs = host_tables.data();          // [r * M + s] -> pair * P, or -1 for an unwanted pair
         long long* rs_of_pair = host_tables.data() + M * M;  // [pair] -> r * M + s
         int64_t pair = 0;
         for (int64_t r = 0; r < M; ++r)
             for (int64_t sI = 0; sI < M; ++sI) {
-                const bool wanted = strict ? r < sI : r <= sI;
+                const bool wanted = sI >= first_s(r);
                 slot_of_rs[r * M + sI] = wanted ? pair * P : -1;
                 if (wanted) rs_of_pair[pair++] = r * M + sI;
             }
@@ -207,11 +311,12 @@ extern "C" int qs_transform_two_body_symmetric(const void* u, int u_dtype, const
     // step 3: rows (r, s, a) -- tiles wanted iff they hold some r < s;  packed store T3p[q, pair(r, s), a]
     const QsTileMask m3 = {2, strict, M * N, M, N, M};
     if ((rc = qs_quarter_transform_masked(bufB, td, M * M * N, N, P, img3, c_dtype, M, bufA, N, 1, 0, 1, 0, npairs * P,
-                                          &m3, lists, dev_slot_of_rs, nullptr, /*xq_even=*/P % 2 == 0, stream)))
+                                          &m3, lists, dev_slot_of_rs, nullptr, /*xq_even=*/P % 2 == 0, 0, stream)))
         return rc;
     // step 4: dense over rows (q, pair);  out[p, q, r, s] at p M^3 + q M^2 + (r M + s)(pair)
     if ((rc = qs_quarter_transform_masked(bufA, td, M * npairs, N, P, img3, c_dtype, M, out, npairs, 0, M * M, 1, 0,
-                                          M * M * M, nullptr, nullptr, nullptr, dev_rs_of_pair, 0, stream)))
+                                          M * M * M, nullptr, nullptr, nullptr, dev_rs_of_pair, 0, /*xr_paired=*/paired,
+                                          stream)))
         return rc;
     return qs_mirror_fill(out, td, M, symmetry, stream);
 }
@@ -241,6 +346,14 @@ extern "C" int qs_transform_one_body(const void* h, int h_dtype, const void* C, 
     const int td = (h_dtype == QS_C128 || c_dtype == QS_C128) ? QS_C128 : QS_F64;
     int64_t img_a, img_b;
     int rc;
+    if (n <= kSmallOneBody && n_new <= kSmallOneBody) {
+        // T[a, q] = sum_b h[a, b] C[b, q]  (n x n_new, dtype td) ; out[p, q] = sum_a Ct[p, a] T[a, q]
+        void* T = workspace;  // n * n_new elements of td (the workspace of the GEMM path below is larger)
+        if ((rc = small_matmul(h, h_dtype, n, 1, 0, C, c_dtype, n_new, T, n_new, n, n_new, n, stream))) return rc;
+        if (Ct) return small_matmul(Ct, c_dtype, n, 1, 0, T, td, n_new, out, n_new, n_new, n_new, n, stream);
+        // Ct = conj(C)^T: element (p, a) = conj(C[a, p])
+        return small_matmul(C, c_dtype, 1, n_new, 1, T, td, n_new, out, n_new, n_new, n_new, n, stream);
+    }
     if ((rc = qs_coeff_image_bytes(n, n_new, h_dtype, c_dtype, &img_a))) return rc;
     if ((rc = qs_coeff_image_bytes(n, n_new, td, c_dtype, &img_b))) return rc;
     const int64_t ph = padded_pitch(n, h_dtype), pt = padded_pitch(n, td);

@@ -185,14 +185,15 @@ class CudaEngine:
         lists.record_stream(torch.cuda.current_stream())
 
     def quarter_scatter_rows(self, A, X, K, lda, image, m_dtype, W, dests, x_inner, sx1, xr_table, w_inner, sw0,
-                             deal=1, tile_start=0):
+                             deal=1, tile_start=0, rows_paired=False):
         if X <= 0:
             return
         table = (ctypes.c_void_p * len(dests))(*[buf.at(off) for buf, off in dests])
         _native.call(
             "qs_quarter_transform_scatter_rows", ctypes.c_void_p(A.at(0)), _CODES[A.dtype], X, K, lda,
             ctypes.c_void_p(image.data_ptr()), _CODES[m_dtype], W, table, len(dests), x_inner, sx1,
-            ctypes.c_void_p(xr_table.data_ptr()), w_inner, sw0, int(deal), int(tile_start), self._stream(),
+            ctypes.c_void_p(xr_table.data_ptr()), w_inner, sw0, int(deal), int(tile_start), int(bool(rows_paired)),
+            self._stream(),
         )
 
     # consumers of a shard (csrc/consumers.cu)
@@ -730,11 +731,18 @@ class _RankTransform:
         cache = self.ctx.__dict__.setdefault("_pair_tables", {})
         key = (self.rank, self.n, m, W, P, self.cyclic)
         if key in cache:
-            (self.npairs, self.step3_tables, self.rs_of_pair, self.rs_of_pair_dev) = cache[key]
+            (self.npairs, self.step3_tables, self.rs_of_pair, self.rs_of_pair_dev, self.rows_paired) = cache[key]
             return
         r = self.r_values()[:, None]
         sI = numpy.arange(m, dtype=numpy.int64)[None, :]
         wanted = cyclic_wanted(r, sI, m)
+        # Real tensors with an even extent: complete every aligned couple (s even, s + 1) that holds a wanted partner.
+        # The extra element of a couple -- (r, r), or a pair whose mirror image the owner of s computes anyway -- is
+        # overwritten by the cyclic fill afterwards; rows 2k and 2k + 1 of step 4 are then neighbours in the result
+        # and cross NVLink as 16-byte stores forming whole lines instead of scattered 8-byte ones.
+        self.rows_paired = self.t_dtype == torch.float64 and m % 2 == 0
+        if self.rows_paired:
+            wanted = wanted | wanted[:, sI[0] ^ 1]
         self.npairs = int(wanted.sum())
         slot = numpy.full((R, m), -1, dtype=numpy.int64)
         slot[wanted] = numpy.arange(self.npairs, dtype=numpy.int64) * P  # row-major (r_loc, s) order
@@ -756,7 +764,7 @@ class _RankTransform:
                     if self.a_off[src + 1] > self.a_off[src]:
                         table = numpy.ascontiguousarray(slot.reshape(-1) + numpy.where(slot.reshape(-1) >= 0, self.a_off[src], 0))
                         self.step3_tables.append((src, table, self.engine.index_table(table)))
-        cache[key] = (self.npairs, self.step3_tables, self.rs_of_pair, self.rs_of_pair_dev)
+        cache[key] = (self.npairs, self.step3_tables, self.rs_of_pair, self.rs_of_pair_dev, self.rows_paired)
 
     def step3_pairs(self, recv_local):
         """T3p[q, pair(r_loc, s), a] = sum_b T2[src][r_loc][s][a_loc][b] C~[q, b] for the wanted pairs only."""
@@ -784,7 +792,7 @@ class _RankTransform:
         dests = [(out[j], 0) for j in range(self.ctx.world)]
         eng.quarter_scatter_rows(self.scratch, m * self.npairs, n, P, self.img4_scatter, self.c_dtype, m, dests,
                                  self.npairs, m * m, self.rs_of_pair_dev, self.r_block, m**3, deal=self.deal,
-                                 tile_start=self.tile_start)
+                                 tile_start=self.tile_start, rows_paired=self.rows_paired)
 
     def step4_local(self, out_local):
         """Collective schedule: u'[p, q, r_loc, s] dense on this rank (sharded on the third index)."""

@@ -151,7 +151,7 @@ class NumpyEngine:
         out.flat()[ax[:, None] + aw[None, :]] = res[keep]
 
     def quarter_scatter_rows(self, A, X, K, lda, image, m_dtype, W, dests, x_inner, sx1, xr_table, w_inner, sw0, deal=1,
-                             tile_start=0):
+                             tile_start=0, rows_paired=False):
         if X <= 0:
             return
         res = self._product(A, X, K, lda, image)
@@ -160,6 +160,8 @@ class NumpyEngine:
             physical[:, (np.arange(W) * deal) % W] = res
             res = physical
         table = xr_table.numpy() if isinstance(xr_table, torch.Tensor) else np.asarray(xr_table)
+        if rows_paired:  # the promise behind the 16-byte stores: rows 2k, 2k + 1 adjacent at an even offset
+            assert x_inner % 2 == 0 and np.all(table[0::2] % 2 == 0) and np.all(table[1::2] == table[0::2] + 1)
         x = np.arange(X)
         ax = (x // x_inner) * sx1 + table[x % x_inner]
         for j, (buf, off) in enumerate(dests):
