@@ -105,42 +105,64 @@ __global__ void __launch_bounds__(256) symmetry_check_kernel(const double* __res
 // Complete out[p,q,r,s] of which only r < s (MODE 1) or r <= s (MODE 2) holds valid data:
 //   MODE 1: out[p,q,s,r] = -out[p,q,r,s] (r < s), out[p,q,r,r] = 0
 //   MODE 2: out[q,p,s,r] =  out[p,q,r,s] (r < s), and out[q,p,r,r] = out[p,q,r,r] for p < q
-// grid (tile pairs tr <= ts, q, p); the block reads the valid tile (tr, ts) and writes the mirrored tile (ts, tr).
+// One block reads the valid tile (tr, ts) and writes the mirrored tile (ts, tr) of kFillPlanes consecutive planes p,
+// keeping the loads of the next plane in flight while it stores the current one (a block that turns over after one
+// 8 KB tile has no loads in flight during its stores: 4.2 TB/s).  grid (tile pairs tr <= ts, q, ceil(m / kFillPlanes)).
+constexpr int kFillPlanes = 4;
+
 template <bool COMPLEX, int MODE>
-__global__ void __launch_bounds__(256) mirror_fill_kernel(double* __restrict__ out, int n, int tiles) {
+__global__ void __launch_bounds__(256) mirror_fill_pipelined_kernel(double* __restrict__ out, int n, int tiles) {
     int tr, ts;
     tile_pair(blockIdx.x, tiles, tr, ts);
-    const int p = blockIdx.z, q = blockIdx.y;
+    const int q = blockIdx.y;
+    const int p_first = blockIdx.z * kFillPlanes;
+    const int p_last = min(p_first + kFillPlanes, n);
     __shared__ double vre[kTile][kTile + 1], vim[COMPLEX ? kTile : 1][kTile + 1];
     const int r0 = tr * kTile, s0 = ts * kTile;
     const int tx = threadIdx.x, ty = threadIdx.y;
-    const long long src = ((long long)p * n + q) * n * n;
-    const long long dst = MODE == 1 ? src : ((long long)q * n + p) * n * n;
-    for (int i = ty; i < kTile; i += 8)
-        if (r0 + i < n && s0 + tx < n) {
-            const Val<COMPLEX> v = Val<COMPLEX>::load(out, src + (long long)(r0 + i) * n + s0 + tx);
-            vre[i][tx] = v.re;
-            if (COMPLEX) vim[i][tx] = v.im;
-        }
-    __syncthreads();
     const double sign = MODE == 1 ? -1.0 : 1.0;
-    // target element (s, r) = (s0 + i, r0 + tx) takes source (r, s) = (r0 + tx, s0 + i), valid iff r < s
-    for (int i = ty; i < kTile; i += 8) {
-        const int s = s0 + i, r = r0 + tx;
-        if (s >= n || r >= n) continue;
-        const long long at = dst + (long long)s * n + r;
-        if (r < s) {
-            if (COMPLEX) reinterpret_cast<double2*>(out)[at] = make_double2(sign * vre[tx][i], sign * vim[tx][i]);
-            else out[at] = sign * vre[tx][i];
-        } else if (MODE == 1 && r == s) {
-            if (COMPLEX) reinterpret_cast<double2*>(out)[at] = make_double2(0.0, 0.0);
-            else out[at] = 0.0;
-        } else if (MODE == 2 && r == s && p < q) {
-            // both out[p,q,r,r] and out[q,p,r,r] were computed; keep one so that the result is EXACTLY symmetric
-            // (the next basis change then finds the symmetry again)
-            if (COMPLEX) reinterpret_cast<double2*>(out)[at] = make_double2(vre[tx][i], vim[tx][i]);
-            else out[at] = vre[tx][i];
+    Val<COMPLEX> cur[kTile / 8], nxt[kTile / 8];
+    auto load = [&](Val<COMPLEX>(&v)[kTile / 8], int p) {
+        const long long src = ((long long)p * n + q) * n * n;
+#pragma unroll
+        for (int k = 0; k < kTile / 8; ++k) {
+            const int i = ty + 8 * k;
+            v[k] = (r0 + i < n && s0 + tx < n) ? Val<COMPLEX>::load(out, src + (long long)(r0 + i) * n + s0 + tx)
+                                               : Val<COMPLEX>{0.0, 0.0};
         }
+    };
+    load(cur, p_first);
+    for (int p = p_first; p < p_last; ++p) {
+#pragma unroll
+        for (int k = 0; k < kTile / 8; ++k) {
+            vre[ty + 8 * k][tx] = cur[k].re;
+            if (COMPLEX) vim[ty + 8 * k][tx] = cur[k].im;
+        }
+        __syncthreads();
+        if (p + 1 < p_last) load(nxt, p + 1);  // in flight during the stores below
+        const long long dst = MODE == 1 ? ((long long)p * n + q) * n * n : ((long long)q * n + p) * n * n;
+        // target element (s, r) = (s0 + i, r0 + tx) takes source (r, s) = (r0 + tx, s0 + i), valid iff r < s
+#pragma unroll
+        for (int k = 0; k < kTile / 8; ++k) {
+            const int i = ty + 8 * k;
+            const int sI = s0 + i, r = r0 + tx;
+            if (sI >= n || r >= n) continue;
+            const long long at = dst + (long long)sI * n + r;
+            if (r < sI) {
+                if (COMPLEX) reinterpret_cast<double2*>(out)[at] = make_double2(sign * vre[tx][i], sign * vim[tx][i]);
+                else out[at] = sign * vre[tx][i];
+            } else if (MODE == 1 && r == sI) {
+                if (COMPLEX) reinterpret_cast<double2*>(out)[at] = make_double2(0.0, 0.0);
+                else out[at] = 0.0;
+            } else if (MODE == 2 && r == sI && p < q) {
+                // both out[p,q,r,r] and out[q,p,r,r] were computed; keep one so that the result is EXACTLY symmetric
+                if (COMPLEX) reinterpret_cast<double2*>(out)[at] = make_double2(vre[tx][i], vim[tx][i]);
+                else out[at] = vre[tx][i];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kTile / 8; ++k) cur[k] = nxt[k];
     }
 }
 
@@ -154,28 +176,49 @@ __host__ __device__ __forceinline__ bool cyclic_wanted(int r, int s, int m) {
 }
 
 // out[p,q,r,s] = -out[p,q,s,r] for every pair the cyclic rule did not compute, out[p,q,r,r] = 0.
-// grid (tiles * tiles, m, planes): the block owns target tile (tr, ts) and reads source tile (ts, tr).
+// grid (tiles * tiles, m, ceil(planes / kFillPlanes)): the block owns target tile (tr, ts) of kFillPlanes consecutive
+// planes p, reads source tile (ts, tr) and keeps the next plane's loads in flight while it stores the current one.
 template <bool COMPLEX>
-__global__ void __launch_bounds__(256) cyclic_fill_kernel(double* __restrict__ out, int n, int tiles) {
+__global__ void __launch_bounds__(256) cyclic_fill_kernel(double* __restrict__ out, int n, int tiles, int planes) {
     const int tr = blockIdx.x / tiles, ts = blockIdx.x % tiles;
     __shared__ double vre[kTile][kTile + 1], vim[COMPLEX ? kTile : 1][kTile + 1];
     const int r0 = tr * kTile, s0 = ts * kTile;
     const int tx = threadIdx.x, ty = threadIdx.y;
-    const long long plane = ((long long)blockIdx.z * n + blockIdx.y) * n * n;
-    for (int i = ty; i < kTile; i += 8)
-        if (s0 + i < n && r0 + tx < n) {
-            const Val<COMPLEX> v = Val<COMPLEX>::load(out, plane + (long long)(s0 + i) * n + r0 + tx);
-            vre[i][tx] = v.re;
-            if (COMPLEX) vim[i][tx] = v.im;
+    const int p_first = blockIdx.z * kFillPlanes;
+    const int p_last = min(p_first + kFillPlanes, planes);
+    Val<COMPLEX> cur[kTile / 8], nxt[kTile / 8];
+    auto load = [&](Val<COMPLEX>(&v)[kTile / 8], int p) {
+        const long long plane = ((long long)p * n + blockIdx.y) * n * n;
+#pragma unroll
+        for (int k = 0; k < kTile / 8; ++k) {
+            const int i = ty + 8 * k;
+            v[k] = (s0 + i < n && r0 + tx < n) ? Val<COMPLEX>::load(out, plane + (long long)(s0 + i) * n + r0 + tx)
+                                               : Val<COMPLEX>{0.0, 0.0};
         }
-    __syncthreads();
-    for (int i = ty; i < kTile; i += 8) {
-        const int r = r0 + i, s = s0 + tx;
-        if (r >= n || s >= n || cyclic_wanted(r, s, n)) continue;
-        const long long at = plane + (long long)r * n + s;
-        const double re = r == s ? 0.0 : -vre[tx][i], im = (COMPLEX && r != s) ? -vim[tx][i] : 0.0;
-        if (COMPLEX) reinterpret_cast<double2*>(out)[at] = make_double2(re, im);
-        else out[at] = re;
+    };
+    load(cur, p_first);
+    for (int p = p_first; p < p_last; ++p) {
+#pragma unroll
+        for (int k = 0; k < kTile / 8; ++k) {
+            vre[ty + 8 * k][tx] = cur[k].re;
+            if (COMPLEX) vim[ty + 8 * k][tx] = cur[k].im;
+        }
+        __syncthreads();
+        if (p + 1 < p_last) load(nxt, p + 1);
+        const long long plane = ((long long)p * n + blockIdx.y) * n * n;
+#pragma unroll
+        for (int k = 0; k < kTile / 8; ++k) {
+            const int i = ty + 8 * k;
+            const int r = r0 + i, sI = s0 + tx;
+            if (r >= n || sI >= n || cyclic_wanted(r, sI, n)) continue;
+            const long long at = plane + (long long)r * n + sI;
+            const double re = r == sI ? 0.0 : -vre[tx][i], im = (COMPLEX && r != sI) ? -vim[tx][i] : 0.0;
+            if (COMPLEX) reinterpret_cast<double2*>(out)[at] = make_double2(re, im);
+            else out[at] = re;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kTile / 8; ++k) cur[k] = nxt[k];
     }
 }
 
@@ -218,11 +261,13 @@ extern "C" int qs_cyclic_antisymmetric_fill(void* out, int dtype, int64_t m, int
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int tiles = (int)qs_ceil_div(m, kTile);
     const dim3 block(32, 8);
-    const dim3 grid((unsigned)(tiles * tiles), (unsigned)m, (unsigned)planes);
+    const dim3 grid((unsigned)(tiles * tiles), (unsigned)m, (unsigned)qs_ceil_div(planes, kFillPlanes));
     int span = -1;
     qs_timing_begin(QS_FAMILY_SPIN_PASS, 1.5 * (double)planes * m * m * m * 8.0 * qs_elem_doubles(dtype), stream, &span);
-    if (dtype == QS_C128) cyclic_fill_kernel<true><<<grid, block, 0, st>>>(static_cast<double*>(out), (int)m, tiles);
-    else cyclic_fill_kernel<false><<<grid, block, 0, st>>>(static_cast<double*>(out), (int)m, tiles);
+    if (dtype == QS_C128)
+        cyclic_fill_kernel<true><<<grid, block, 0, st>>>(static_cast<double*>(out), (int)m, tiles, (int)planes);
+    else
+        cyclic_fill_kernel<false><<<grid, block, 0, st>>>(static_cast<double*>(out), (int)m, tiles, (int)planes);
     QS_LAUNCH_CHECK();
     qs_timing_end(span, stream);
     return QS_OK;
@@ -273,16 +318,16 @@ int qs_mirror_fill(void* out, int dtype, int64_t m, int mode, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int tiles = (int)qs_ceil_div(m, kTile);
     const dim3 block(32, 8);
-    const dim3 grid((unsigned)(tiles * (tiles + 1) / 2), (unsigned)m, (unsigned)m);
+    const dim3 grid((unsigned)(tiles * (tiles + 1) / 2), (unsigned)m, (unsigned)qs_ceil_div(m, kFillPlanes));
     double* o = static_cast<double*>(out);
     int span = -1;
     qs_timing_begin(QS_FAMILY_SPIN_PASS, (double)m * m * m * m * 8.0 * qs_elem_doubles(dtype), stream, &span);
     if (dtype == QS_C128) {
-        if (mode == 1) mirror_fill_kernel<true, 1><<<grid, block, 0, st>>>(o, (int)m, tiles);
-        else mirror_fill_kernel<true, 2><<<grid, block, 0, st>>>(o, (int)m, tiles);
+        if (mode == 1) mirror_fill_pipelined_kernel<true, 1><<<grid, block, 0, st>>>(o, (int)m, tiles);
+        else mirror_fill_pipelined_kernel<true, 2><<<grid, block, 0, st>>>(o, (int)m, tiles);
     } else {
-        if (mode == 1) mirror_fill_kernel<false, 1><<<grid, block, 0, st>>>(o, (int)m, tiles);
-        else mirror_fill_kernel<false, 2><<<grid, block, 0, st>>>(o, (int)m, tiles);
+        if (mode == 1) mirror_fill_pipelined_kernel<false, 1><<<grid, block, 0, st>>>(o, (int)m, tiles);
+        else mirror_fill_pipelined_kernel<false, 2><<<grid, block, 0, st>>>(o, (int)m, tiles);
     }
     QS_LAUNCH_CHECK();
     qs_timing_end(span, stream);
