@@ -139,6 +139,18 @@ int qs_quarter_transform_scatter(const void* A, int a_dtype, int64_t X, int64_t 
                                  int64_t w_inner, int64_t sw0, int64_t w_deal, int w_cyclic,
                                  int64_t tile_start, void* stream);
 
+/* The scattering store of the anti-symmetric schedule's first exchange: cyclic destinations (column r goes to
+ * host_out_table[r % n_dest], column r / n_dest there, stride sw0), restricted to the CTA tiles that hold a pair
+ * (r, s) the cyclic pair rule wants -- s = (x / rows_per_s) % W is the row's second index; `padded` != 0 also keeps
+ * the other member s ^ 1 of an aligned couple (the padded pair lists of real tensors).  About a third of the tiles
+ * of this step, and of its NVLink traffic, go away.  list_ws: qs_quarter_tile_list_bytes() bytes of device memory. */
+int qs_quarter_transform_scatter_pairs(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda,
+                                       const void* image, int m_dtype, int64_t W,
+                                       void* const* host_out_table, int64_t n_dest, int64_t x_inner,
+                                       int64_t x_mid, int64_t sx0, int64_t sx1, int64_t sx2, int64_t sw0,
+                                       int64_t rows_per_s, int padded, void* list_ws, int64_t list_ws_bytes,
+                                       void* stream);
+
 /* Epilogue of the quarter GEMM.  Besides storing from registers, a launch can stage each warp's accumulator tile
  * in shared memory ([column][row], 16 real columns at a time, two 4 KiB buffers per warp) and hand every run of rows
  * that is contiguous in the output to the copy engine (cp.async.bulk shared -> global, SASS UBLKCP.G.S), going on

@@ -71,8 +71,21 @@ uint64_t qs_hash_bytes(const void* data, size_t bytes, uint64_t seed);
 
 // Internal (not part of the C ABI): symmetry mask of a quarter transform (see quarter_gemm.cu, tile_wanted) and
 // the masked launch used by the symmetry-aware four-index transform (transform.cu).
+// Which of the two ordered pairs (r, s), (s, r) the SHARDED symmetry-aware transform computes: the one whose
+// cyclic distance d = (s - r) mod m is the shorter (ties, 2 d = m, go to r < s).  Every r then has the same number
+// of partners s, so any partition of r over the ranks stays balanced.
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+static inline bool qs_cyclic_wanted(long long r, long long s, long long m) {
+    const long long d = s >= r ? s - r : s - r + m;
+    return d > 0 && (2 * d < m || (2 * d == m && r < s));
+}
+
 struct QsTileMask {
-    int kind;             // 0 none; 1 column < row_lo; 2 row_hi < row_lo
+    int kind;             // 0 none; 1 column < row_lo; 2 row_hi < row_lo; 3 cyclic pair rule on (column, row_lo):
+                          //   wanted iff qs_cyclic_wanted(column, row_lo, ml), or (strict == 0) the same with the
+                          //   other member row_lo ^ 1 of the aligned couple (the padded pair lists of the real case)
     int strict;           // 1: "<", 0: "<="
     int64_t dh, mh, dl, ml;  // row_hi(x) = (x / dh) % mh, row_lo(x) = (x / dl) % ml
 };

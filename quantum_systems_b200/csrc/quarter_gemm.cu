@@ -1100,8 +1100,18 @@ namespace {
 //   kind 2: wanted iff row_hi < row_lo (or <=),  row_hi(x) = (x / dh) % mh,  dl divides dh
 // Conservative (never drops a wanted tile); exact when a tile does not straddle a block of the coarser index.
 bool tile_wanted(const QsTileMask& m, int64_t x0, int64_t x1, int64_t w0, int64_t w1) {
-    (void)w1;
     const int64_t l0 = x0 / m.dl, l1 = x1 / m.dl;
+    if (m.kind == 3) {
+        // every (row_lo, column) of the tile against the cyclic pair rule; a tile holds one or two values of row_lo
+        // (128 rows) and at most 64 columns, so brute force is cheap -- and exact
+        const int64_t blocks = l1 - l0 + 1 < m.ml ? l1 - l0 + 1 : m.ml;
+        for (int64_t b = 0; b < blocks; ++b) {
+            const int64_t s = (l0 + b) % m.ml;
+            for (int64_t r = w0; r <= w1 && r < m.ml; ++r)
+                if (qs_cyclic_wanted(r, s, m.ml) || (!m.strict && qs_cyclic_wanted(r, s ^ 1, m.ml))) return true;
+        }
+        return false;
+    }
     int64_t lo_max;  // the largest row_lo inside the tile
     if (l1 - l0 >= m.ml - 1 || (l1 % m.ml) < (l0 % m.ml)) lo_max = m.ml - 1;  // covers a whole period or wraps
     else lo_max = l1 % m.ml;
@@ -1315,7 +1325,7 @@ int quarter_launch(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda
     memset(&cached, 0, sizeof(cached));
     bool lists_cached = false;
     if (masked) {
-        QS_REQUIRE(list_ws && w_deal == 1 && n_dest == 0, "qs_quarter_transform: a masked launch needs list space");
+        QS_REQUIRE(list_ws && w_deal == 1, "qs_quarter_transform: a masked launch needs list space and undealt columns");
         lists_cached = planned_lists(tl, a_dtype, m_dtype, X, x_inner, K, W, out_complex, mask, host_xq_table, &cached,
                                      lists);
         wanted_fraction = cached.fraction;
@@ -1470,6 +1480,25 @@ extern "C" int qs_quarter_transform_scatter_rows(const void* A, int a_dtype, int
     return quarter_launch(A, a_dtype, X, K, lda, image, m_dtype, W, nullptr, host_out_table, n_dest, x_inner,
                           0xFFFFFFFFLL, 0, sx1, 0, w_inner, sw0, 0, w_deal, stream, nullptr, nullptr, nullptr,
                           reinterpret_cast<const long long*>(xr_table), nullptr, 0, 0, tile_start, rows_paired);
+}
+
+// The scattering store restricted to the CTA tiles that hold a pair (column r, row index s) the cyclic pair rule of
+// the anti-symmetric schedule wants (mask kind 3: s = (x / rows_per_s) % W; `padded` != 0 also keeps the other member
+// s ^ 1 of an aligned couple, matching the padded pair lists of the real case).  Columns are undealt (cyclic
+// destinations).  list_ws: qs_quarter_tile_list_bytes() bytes of device memory (used only if the table cache is full).
+extern "C" int qs_quarter_transform_scatter_pairs(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda,
+                                                  const void* image, int m_dtype, int64_t W,
+                                                  void* const* host_out_table, int64_t n_dest, int64_t x_inner,
+                                                  int64_t x_mid, int64_t sx0, int64_t sx1, int64_t sx2, int64_t sw0,
+                                                  int64_t rows_per_s, int padded, void* list_ws,
+                                                  int64_t list_ws_bytes, void* stream) {
+    QS_REQUIRE(host_out_table && n_dest > 0 && list_ws, "qs_quarter_transform_scatter_pairs: null pointer");
+    QS_REQUIRE(X > 0 && K > 0 && W > 0 && rows_per_s > 0 &&
+                   list_ws_bytes >= qs_tile_list_bytes(X, K, W, a_dtype, m_dtype),
+               "qs_quarter_transform_scatter_pairs: bad extents or tile-list space too small");
+    const QsTileMask mask = {3, padded ? 0 : 1, 1, 1, rows_per_s, W};
+    return quarter_launch(A, a_dtype, X, K, lda, image, m_dtype, W, nullptr, host_out_table, n_dest, x_inner, x_mid, sx0,
+                          sx1, sx2, 1, sw0, 0, 1, stream, &mask, list_ws, nullptr, nullptr, nullptr, 0, /*w_cyclic=*/1);
 }
 
 extern "C" int qs_quarter_transform(const void* A, int a_dtype, int64_t X, int64_t K, int64_t lda, const void* image,

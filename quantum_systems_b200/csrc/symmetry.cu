@@ -166,14 +166,7 @@ __global__ void __launch_bounds__(256) mirror_fill_pipelined_kernel(double* __re
     }
 }
 
-// Which of the two ordered pairs (r, s), (s, r) the SHARDED symmetry-aware transform computes: the one whose
-// cyclic distance d = (s - r) mod m is the shorter (ties, 2 d = m, go to r < s).  Every r then has the same number
-// of partners s, so the contiguous r-partition of the ranks stays balanced (r < s would give rank 0 fifteen times
-// the pairs of rank 7).
-__host__ __device__ __forceinline__ bool cyclic_wanted(int r, int s, int m) {
-    const int d = s >= r ? s - r : s - r + m;
-    return d > 0 && (2 * d < m || (2 * d == m && r < s));
-}
+__host__ __device__ __forceinline__ bool cyclic_wanted(int r, int s, int m) { return qs_cyclic_wanted(r, s, m); }
 
 // out[p,q,r,s] = -out[p,q,s,r] for every pair the cyclic rule did not compute, out[p,q,r,r] = 0.
 // grid (tiles * tiles, m, ceil(planes / kFillPlanes)): the block owns target tile (tr, ts) of kFillPlanes consecutive

@@ -196,6 +196,23 @@ class CudaEngine:
             self._stream(),
         )
 
+    def quarter_scatter_pairs(self, A, X, K, lda, image, m_dtype, W, dests, x_inner, x_mid, sx0, sx1, sx2, sw0,
+                              rows_per_s, padded):
+        """The first exchange of the anti-symmetric schedule: cyclic destinations, only the tiles that hold a pair
+        (r, s) the cyclic pair rule wants (qs_quarter_transform_scatter_pairs)."""
+        if X <= 0:
+            return
+        nbytes = ctypes.c_int64(0)
+        _native.call("qs_quarter_tile_list_bytes", X, K, W, _CODES[A.dtype], _CODES[m_dtype], ctypes.byref(nbytes))
+        lists = torch.empty(nbytes.value, dtype=torch.uint8, device="cuda")
+        table = (ctypes.c_void_p * len(dests))(*[buf.at(off) for buf, off in dests])
+        _native.call(
+            "qs_quarter_transform_scatter_pairs", ctypes.c_void_p(A.at(0)), _CODES[A.dtype], X, K, lda,
+            ctypes.c_void_p(image.data_ptr()), _CODES[m_dtype], W, table, len(dests), x_inner, max(x_mid, 1), sx0, sx1,
+            sx2, sw0, rows_per_s, int(bool(padded)), ctypes.c_void_p(lists.data_ptr()), nbytes.value, self._stream(),
+        )
+        lists.record_stream(torch.cuda.current_stream())
+
     # consumers of a shard (csrc/consumers.cu)
     def extract_block(self, buf, planes, n, bounds):
         (a0, a1), (b0, b1), (c0, c1), (d0, d1) = bounds
@@ -657,10 +674,11 @@ class _RankTransform:
             src = padded
         eng.quarter(src, A * n * n, n, self.Pu, self.img1, self.c_dtype, m, self.scratch, 0, n, 1, P, 1, 0, A * n * P)
 
-    def step2_scatter(self, recv):
+    def step2_scatter(self, recv, pairs_only=False):
         """T2[r, s, a, b] = sum_c T1[s, a_loc, b, c] C[c, r], stored into the rank that owns r (cyclic: r % W) at
         [src = this rank][r_loc = r // W][s][a_loc][b] (b at pitch P): the a -> r re-partition rides on the epilogue,
-        and this rank's tiles fill ONE contiguous region of every destination."""
+        and this rank's tiles fill ONE contiguous region of every destination.  ``pairs_only`` (anti-symmetric u):
+        only the tiles that hold a pair (r, s) which steps 3 and 4 will use are computed and sent."""
         eng, n, m, A, P = self.engine, self.n, self.m, self.A, self.P
         a0 = self.a_off[self.rank]
         if not self.cyclic:  # interleaved layout: [r_loc][s][a][b], this rank's planes between the others'
@@ -670,6 +688,10 @@ class _RankTransform:
             return
         # region of this source in destination j: behind the regions of the sources before it
         dests = [(recv[j], a0 * self.r_count(j) * m * P) for j in range(self.ctx.world)]
+        if pairs_only and not self.tile_start:
+            eng.quarter_scatter_pairs(self.scratch, m * A * n, n, P, self.img2, self.c_dtype, m, dests, n, A, 1, P,
+                                      A * P, m * A * P, A * n, self.pairs_padded())
+            return
         eng.quarter_scatter(self.scratch, m * A * n, n, P, self.img2, self.c_dtype, m, dests, n, A, 1, P, A * P,
                             0, m * A * P, deal=1, cyclic=True, tile_start=self.tile_start)
 
@@ -722,6 +744,10 @@ class _RankTransform:
                             m * m, self.r_block, m**3, deal=self.deal, tile_start=self.tile_start)
 
     # ---- anti-symmetric u: steps 3 and 4 on half of the (r, s) pairs (cyclic rule), packed by pair -------------
+    def pairs_padded(self):
+        """Real tensors with an even extent pad the pair lists to aligned couples (s even, s + 1), see prepare_pairs."""
+        return self.t_dtype == torch.float64 and self.m % 2 == 0
+
     def prepare_pairs(self):
         """Pair tables of this rank: for every owned r the partners s the cyclic-distance rule assigns to (r, s)."""
         import numpy
@@ -740,7 +766,7 @@ class _RankTransform:
         # The extra element of a couple -- (r, r), or a pair whose mirror image the owner of s computes anyway -- is
         # overwritten by the cyclic fill afterwards; rows 2k and 2k + 1 of step 4 are then neighbours in the result
         # and cross NVLink as 16-byte stores forming whole lines instead of scattered 8-byte ones.
-        self.rows_paired = self.t_dtype == torch.float64 and m % 2 == 0
+        self.rows_paired = self.pairs_padded()
         if self.rows_paired:
             wanted = wanted | wanted[:, sI[0] ^ 1]
         self.npairs = int(wanted.sum())
@@ -860,7 +886,7 @@ def transform_two_body_sharded(u, C, C_tilde=None, symmetry=None):
         ctx.barrier()  # every rank is done with whatever it last read from these buffers
         for r, w in work.items():
             w.step1(u.buffers[r][r])
-            w.step2_scatter(recv[r])
+            w.step2_scatter(recv[r], pairs_only=bool(symmetry))
         ctx.barrier()  # all tiles of T2 have landed
         for r, w in work.items():
             if symmetry:

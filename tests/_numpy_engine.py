@@ -95,6 +95,42 @@ class NumpyEngine:
                 continue
             buf.flat()[off + ax[:, None] + aw[None, :]] = res[:, cols]
 
+    def quarter_scatter_pairs(self, A, X, K, lda, image, m_dtype, W, dests, x_inner, x_mid, sx0, sx1, sx2, sw0,
+                              rows_per_s, padded):
+        """qs_quarter_transform_scatter_pairs: cyclic destinations, and ONLY the CTA tiles the library's own host-side
+        planner (qs_quarter_plan_tiles, mask kind 3; no device involved) would launch are written -- everything else
+        keeps the NaN the buffers were created with, so a later read of a tile that was never sent shows up."""
+        import ctypes
+
+        from quantum_systems_b200 import _native
+
+        if X <= 0:
+            return
+        lib = _native.load()
+        code = {torch.float64: 0, torch.complex128: 1}
+        args = (X, K, W, code[A.dtype], code[m_dtype], x_inner, 3, 0 if padded else 1, 1, 1, rows_per_s, W,
+                ctypes.c_void_p(0))
+        count = ctypes.c_int64(0)
+        assert lib.qs_quarter_plan_tiles(*args, ctypes.c_void_p(0), 0, ctypes.byref(count)) == 0
+        tiles = np.zeros((count.value, 4), dtype=np.int64)
+        assert lib.qs_quarter_plan_tiles(*args, ctypes.c_void_p(tiles.ctypes.data), count.value, ctypes.byref(count)) == 0
+        res = self._product(A, X, K, lda, image)
+        launched = np.zeros((X, W), dtype=bool)
+        for x0, x1, w0, w1 in tiles:
+            launched[x0 : x1 + 1, w0 : w1 + 1] = True
+        x = np.arange(X)
+        xq = x // x_inner
+        ax = (xq // max(x_mid, 1)) * sx2 + (xq % max(x_mid, 1)) * sx1 + (x % x_inner) * sx0
+        n_dest = len(dests)
+        for j, (buf, off) in enumerate(dests):
+            cols = np.arange(j, W, n_dest)
+            if len(cols) == 0:
+                continue
+            aw = (cols // n_dest) * sw0
+            flat = buf.flat()
+            rows, cidx = np.nonzero(launched[:, cols])
+            flat[off + ax[rows] + aw[cidx]] = res[rows, cols[cidx]]
+
     # consumers of a shard: documented semantics of qs_extract_block / qs_scale_add / qs_occupied_traces
     def extract_block(self, buf, planes, n, bounds):
         (a0, a1), (b0, b1), (c0, c1), (d0, d1) = bounds

@@ -188,8 +188,8 @@ def test_emulated_symmetry_aware_sharded_transform(world, n, m, u_complex, c_com
     assert_close_scaled(plain.gather().cpu().numpy(), expected, rel=1e-12)
 
 
-@pytest.mark.parametrize("world,complex_", [(4, False), (3, True)])
-def test_sharded_odqd_general_system_against_the_closed_form(world, complex_):
+@pytest.mark.parametrize("world,complex_,l", [(4, False, 26), (3, True, 26), (2, False, 66), (8, False, 68)])
+def test_sharded_odqd_general_system_against_the_closed_form(world, complex_, l):
     """The pipeline of BASELINE configs[3]/[4] in miniature (emulated ranks): ShardedBasisSet.from_odqd (sharded grid
     build -> add_spin + anti-symmetrise) -> change_basis twice -> Fock matrix, checked against the closed form of
     the ODQD-structured tensor (tests/closed_form.py) exactly as bench.py checks the full-size runs, and against
@@ -198,7 +198,7 @@ def test_sharded_odqd_general_system_against_the_closed_form(world, complex_):
     from quantum_systems_b200 import sharded
     from quantum_systems_b200.potentials import HOPotential
 
-    l, G = 26, 105
+    G = 4 * l + 1  # l = 66, 68: several column tiles per launch, so the first exchange really skips tiles
     n = 2 * l
     dtype = torch.complex128 if complex_ else torch.float64
     ctx = sharded.EmulatedContext(world)
@@ -214,9 +214,11 @@ def test_sharded_odqd_general_system_against_the_closed_form(world, complex_):
     # explicit reference pipeline at this size
     grid, eps, Lg = oracle.odqd_orbitals(l, 8.0, G, HOPotential(0.5))
     np.testing.assert_allclose(np.abs(Lg), np.abs(basis.grid_coefficients), atol=1e-12)
-    spin = oracle.anti_symmetrize_u(oracle.add_spin_two_body(np.ascontiguousarray(
-        oracle.odqd_coulomb_elements(basis.grid_coefficients, grid, 1.0, 0.25))))
-    assert_close_scaled(basis.u.gather().cpu().numpy(), spin.astype(np.complex128 if complex_ else np.float64))
+    small = l <= 30  # the explicit oracle pipeline next to the closed form (seconds at n = 52, minutes at n = 132)
+    if small:
+        spin = oracle.anti_symmetrize_u(oracle.add_spin_two_body(np.ascontiguousarray(
+            oracle.odqd_coulomb_elements(basis.grid_coefficients, grid, 1.0, 0.25))))
+        assert_close_scaled(basis.u.gather().cpu().numpy(), spin.astype(np.complex128 if complex_ else np.float64))
 
     basis.change_basis(dev(C), None if Ct is None else dev(Ct))
     form = closed_form.SpinDoubledClosedForm(basis.grid_coefficients, W, C, Ct)
@@ -224,7 +226,8 @@ def test_sharded_odqd_general_system_against_the_closed_form(world, complex_):
         p0, p1 = basis.u.planes(r)
         errs = closed_form.check_shard(closed_form.TorchSlab(basis.u.local(r)), p0, form, np.random.default_rng(r), samples=500)
         assert max(errs[:2]) <= 1e-12 * errs[3] and errs[2] == 0.0
-    assert_close_scaled(basis.u.gather().cpu().numpy(), oracle.transform_two_body_elements(spin, C, Ct))
+    if small:
+        assert_close_scaled(basis.u.gather().cpu().numpy(), oracle.transform_two_body_elements(spin, C, Ct))
     # second call of the chain: no new symmetry test, net transform C C / C~ C~
     basis.change_basis(dev(C), None if Ct is None else dev(Ct))
     Ct1 = C.conj().T if Ct is None else Ct

@@ -116,6 +116,28 @@ def test_emulated_symmetry_aware_schedule_matches_oracle(world, n, m, complex_):
         np.testing.assert_allclose(out2.gather().numpy(), expected2, rtol=1e-11, atol=1e-11 * np.abs(expected2).max())
 
 
+@pytest.mark.parametrize("world,n", [(3, 72), (2, 70)])
+def test_symmetry_aware_schedule_with_many_tiles(world, n):
+    """Large enough for several row AND column tiles per launch: the first exchange sends only the tiles that hold a
+    wanted pair (the stand-in writes exactly the tiles the library's planner lists; everything else stays NaN), and
+    steps 3 and 4 must never touch what was not sent."""
+    from quantum_systems_b200 import sharded
+
+    rng = np.random.default_rng(n)
+    u = rng.standard_normal((n,) * 4)
+    u = u - u.transpose(0, 1, 3, 2)
+    C = np.linalg.qr(rng.standard_normal((n, n)))[0]
+    ctx = sharded.EmulatedContext(world, engine=NumpyEngine())
+    basis = sharded.ShardedBasisSet.from_global(ctx, np.eye(n), np.eye(n), u)
+    out = sharded.transform_two_body_sharded(basis.u, torch.from_numpy(C))  # n >= 48: found anti-symmetric, exploited
+    assert out.proven_antisymmetric
+    got = out.gather().numpy()
+    assert not np.isnan(got).any()
+    expected = oracle.transform_two_body_elements(u, C)
+    np.testing.assert_allclose(got, expected, rtol=1e-12, atol=1e-12 * np.abs(expected).max())
+    np.testing.assert_array_equal(got, -got.transpose(0, 1, 3, 2))
+
+
 def test_recycled_handle_raises_instead_of_showing_new_data():
     """A transform writes into the buffers of the tensor replaced one call earlier (ping-pong).  A caller that
     still holds that older handle must get an error, not silently the newer tensor; copy() keeps data alive."""

@@ -96,3 +96,26 @@ def test_row_table_plan_of_the_sharded_step3(lib, n, m, world, rank):
         assert kept_rows[x0 : x1 + 1].any()
     if n >= 50:
         assert launched_rows.mean() < 0.75
+
+
+@pytest.mark.parametrize("padded", [0, 1])
+@pytest.mark.parametrize("dtypes", [(F64, F64), (C128, C128), (C128, F64)])
+@pytest.mark.parametrize("n,m,planes", [(5, 7, 2), (16, 16, 4), (20, 66, 5), (40, 130, 3), (24, 200, 6), (9, 400, 1)])
+def test_first_exchange_mask_cyclic_pairs(lib, n, m, planes, dtypes, padded):
+    """First exchange of the sharded anti-symmetric schedule (mask kind 3): rows (s, a_loc, b), column r; wanted iff
+    the cyclic pair rule computes (r, s) -- or, padded, the other member s ^ 1 of its aligned couple."""
+    from quantum_systems_b200.sharded import cyclic_wanted
+
+    X = m * planes * n
+    tiles = plan(lib, X, n, m, *dtypes, x_inner=n, kind=3, strict=0 if padded else 1, dl=planes * n, ml=m)
+    s = (np.arange(X) // (planes * n))[:, None]
+    r = np.arange(m)[None, :]
+    wanted = cyclic_wanted(r, s, m)
+    if padded:
+        wanted = wanted | cyclic_wanted(r, s ^ 1, m)
+    grid = covered(tiles, X, m)
+    assert not (wanted & ~grid).any(), "a wanted (row, column) pair is in no launched tile"
+    if m >= 200 and planes * n >= 128:  # several column tiles: roughly half of them hold no wanted pair
+        assert grid.mean() < 0.8
+    for t in range(m):  # the library's rule is the schedule's rule
+        assert lib.qs_cyclic_pair_wanted(3 % m, t, m) == int(cyclic_wanted(3 % m, t, m))
