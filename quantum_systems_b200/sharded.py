@@ -4,10 +4,11 @@ Once ``u`` no longer fits one GPU (n >~ 300 spin-orbitals) it is block-partition
 index, ``ceil(n / W)`` planes per rank.  The four-index transform of
 ``BasisSet.transform_two_body_elements`` (reference basis_set.py:336-350) then runs as
 
-    u[a_loc,b,c,d] --C--> T1[s,a_loc,b,c] --C--> T2[r,s,a_loc,b]      steps 1-2: local contractions
-                                              \\=> T2[r_loc,s,a,b]     re-partition a -> r (exchange)
-    T2[r_loc,s,a,b] --C~--> T3[q,r_loc,s,a] --C~--> u'[p,q,r_loc,s]   steps 3-4: local contractions
-                                              \\=> u'[p_loc,q,r,s]     re-partition r -> p (exchange)
+    u[a_loc,b,c,d] --C--> T1[s,a_loc,b,c] --C--> T2[r,s,a_loc,b]           steps 1-2: local contractions
+                                   \\=> T2[src][r_loc][s][a_loc][b]         re-partition a -> r (exchange; r dealt
+                                                                           cyclically, tiles kept source-major)
+    T2[src][r_loc][s][a_loc][b] --C~--> T3[q,r_loc,s,a] --C~--> u'[p,q,r,s]  steps 3-4: local contractions
+                                   \\=> u'[p_loc,q,r,s]                     re-partition r -> p (exchange)
 
 like the transpose steps of a distributed FFT.  Both exchanges are FUSED into the producing GEMM: the
 epilogue of steps 2 and 4 stores every tile straight into the buffer of the rank that owns it, through
@@ -17,9 +18,10 @@ handles), for stream-ordered barriers and for the tiny all-gather of the Fock ma
 carries tensor data on this path.  ``exchange="collective"`` selects the plain
 ``all_to_all_single`` schedule instead (validation, and CPU/gloo tests of the partition logic).
 
-An exactly anti-symmetric ``u`` (every spin-doubled, anti-symmetrised tensor) is detected on the device and
-transformed with steps 3-4 on half of the (r, s) pairs (``cyclic_wanted`` keeps the ranks balanced); see
-``transform_two_body_sharded`` and DESIGN.md section 4.9.
+An exactly anti-symmetric ``u`` (every spin-doubled, anti-symmetrised tensor) is known from its producer or detected
+on the device and transformed with steps 3-4 on half of the (r, s) pairs (``cyclic_wanted`` keeps the ranks
+balanced) and with a first exchange that sends only the tiles holding such a pair; see
+``transform_two_body_sharded`` and DESIGN.md sections 4.9 and 5.
 
 One process per GPU drives one rank (``ProcessContext``).  ``EmulatedContext`` drives all W ranks
 from one process on one device; it exists to test the schedule and the scattering kernel on a
@@ -31,6 +33,7 @@ check the schedule under gloo without a GPU.
 """
 
 import ctypes
+import os
 import weakref
 
 import torch
@@ -57,10 +60,8 @@ EXPLOIT_SYMMETRY = True
 # and source-major T2; "interleaved" = block partition of r and T2[r_loc][s][a][b] (the round-1 layout).
 # ROTATE_TILES: every rank starts its walk over the tiles of a scattering launch at a different place (rank / world
 # of the way through), so that the ranks are never in the same block of a destination at the same time.
-import os as _os
-
-SCATTER_LAYOUT = _os.environ.get("QS_SHARD_LAYOUT", "source_major")
-ROTATE_TILES = _os.environ.get("QS_SHARD_ROTATE", "0") == "1"
+SCATTER_LAYOUT = os.environ.get("QS_SHARD_LAYOUT", "source_major")
+ROTATE_TILES = os.environ.get("QS_SHARD_ROTATE", "0") == "1"
 
 
 def cyclic_wanted(r, s, m):
