@@ -486,7 +486,7 @@ def run_single(args, torch, lib):
         with open(prof) as fh:
             traffic = json.load(fh).get(f"n{n}", {}).get("dram_bytes_per_launch")
     roofline = roofline_entry(kernel, ms, peak_tflops, 2.0 * n**5, 2.0 * 8 * n**4, traffic)
-    roofline["traffic_source"] = "ncu --set full capture of one full-step launch (profiles/quarter_gemm_traffic.json)"
+    roofline["traffic_source"] = "ncu --set full capture of one full-step launch (profiles/quarter_gemm_traffic.json <- profiles/r02r_ncu_round2_n128_summary.csv)"
 
     # ---- CPU baseline (numpy oracle on this box's host cores) and parity of the timed path -------------------
     cpu_baseline = None
