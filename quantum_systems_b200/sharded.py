@@ -62,6 +62,8 @@ EXPLOIT_SYMMETRY = True
 # of the way through), so that the ranks are never in the same block of a destination at the same time.
 SCATTER_LAYOUT = os.environ.get("QS_SHARD_LAYOUT", "source_major")
 ROTATE_TILES = os.environ.get("QS_SHARD_ROTATE", "0") == "1"
+# False (QS_SHARD_MASK=0): the first exchange of the anti-symmetric schedule sends every tile, as in round 1.
+MASK_FIRST_EXCHANGE = os.environ.get("QS_SHARD_MASK", "1") != "0"
 
 
 def cyclic_wanted(r, s, m):
@@ -689,7 +691,7 @@ class _RankTransform:
             return
         # region of this source in destination j: behind the regions of the sources before it
         dests = [(recv[j], a0 * self.r_count(j) * m * P) for j in range(self.ctx.world)]
-        if pairs_only and not self.tile_start:
+        if pairs_only and MASK_FIRST_EXCHANGE and not self.tile_start:
             eng.quarter_scatter_pairs(self.scratch, m * A * n, n, P, self.img2, self.c_dtype, m, dests, n, A, 1, P,
                                       A * P, m * A * P, A * n, self.pairs_padded())
             return
